@@ -1,0 +1,164 @@
+/*
+ * tracs_b200.h -- C ABI of libtracs_b200.so, the B200 (sm_100a) implementation of the TRACS
+ * pairwise-distance hot path. Plain pointers and sizes only; no torch / pybind types.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * gtonkinhill/tracs source tree). The Python module `TRACS` the reference callers import
+ * (tracs/distance.py:8, tracs/transcluster.py:2, tracs/align.py:21) is a thin binding over these
+ * calls: tracs_b200/dropin/TRACS.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; tracs_last_error() then holds a
+ *     message (thread-local). CUDA errors are reported the same way. There is NO CPU fallback:
+ *     without a usable CUDA device the compute entry points fail.
+ *   - result arrays are allocated by the library and released with tracs_edges_free().
+ *   - inputs are borrowed for the duration of the call only.
+ *   - one call at a time per process (like the reference module, which holds the GIL and uses
+ *     function-static caches: src/pairsnp.hpp:19,43).
+ */
+#ifndef TRACS_B200_H
+#define TRACS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Sparse (COO) result of a pair sweep == the 6-tuple returned by pairsnp()
+ * (src/pairsnp.hpp:320-322,457): rows, cols, distances, seq_names, filt_distances,
+ * n_compared_sites, all in (row, col) lexicographic order (src/pairsnp.hpp:395,450-457).
+ * p0_log / eK are filled only by the fused entry points when sampling days are supplied
+ * (what tracs/transcluster.py:8-41 + src/transcluster.hpp:240-287 compute per edge). */
+typedef struct tracs_edges {
+  size_t n_edges;
+  uint64_t *rows;    /* sample index i                                   */
+  uint64_t *cols;    /* sample index j                                   */
+  uint64_t *dist;    /* SNP distance d(i,j)                              */
+  uint64_t *filt;    /* recombination-filtered distance (zeros if !filter) */
+  uint64_t *ncomp;   /* compared (non-N) sites                           */
+  double *p0_log;    /* log P(direct transmission)   or NULL             */
+  double *eK;        /* E[# intermediate hosts]       or NULL             */
+  double *datediff;  /* |t_i - t_j| in years          or NULL             */
+  size_t n_names;
+  char **names;      /* n_names NUL-terminated strings, or NULL           */
+  uint64_t seq_length;
+} tracs_edges_t;
+
+/* Per-call statistics of the last sweep on this thread (for bench.py / roofline accounting). */
+typedef struct tracs_stats {
+  uint64_t n_samples, seq_length;
+  uint64_t n_variable_sites; /* V_eff: sites kept by the exact drop rule     */
+  uint64_t n_words;          /* ceil(V_eff/32) padded to the k-chunk                        */
+  uint64_t n_tiles;          /* 128x128 pair tiles swept                                    */
+  uint64_t n_pairs;          /* pairs in range (what the reference loop visits)             */
+  uint64_t n_edges;
+  uint64_t kernel_launches;  /* kernels of this library launched by the call                */
+  uint64_t h2d_bytes, d2h_bytes;
+  float ms_pack;             /* ASCII -> column masks + N planes (K0a)                      */
+  float ms_compact;          /* variable-site selection + bit-plane gather (K0b)            */
+  float ms_sweep;            /* pair tile sweep incl. threshold/compaction epilogue (K1)    */
+  float ms_sort;             /* edge ordering                                               */
+  float ms_ncomp;            /* compared-sites kernel (K2)                                  */
+  float ms_trans;            /* transmission LUT + gather (K3)                              */
+  float ms_total;            /* device time of the whole call (events on the call's stream) */
+} tracs_stats_t;
+
+/* Options shared by the matrix-input entry points. Zero-initialise, then set. */
+typedef struct tracs_opts {
+  int32_t dist;        /* keep pairs with d <= dist  (pairsnp arg `dist`, int; INT32_MAX = all) */
+  int32_t filter;      /* pairsnp arg `filter` (recombination filter, src/pairsnp.hpp:251-318)  */
+  uint64_t i_end;      /* rows are samples [0, i_end)              (src/pairsnp.hpp:348,382)    */
+  uint64_t j_start;    /* cols are samples [max(j_start,i+1), n)   (src/pairsnp.hpp:354-358,395)*/
+  int32_t shard_rank;  /* this process sweeps row-blocks dealt to shard_rank of shard_world       */
+  int32_t shard_world; /* (0 or 1 = everything). No inter-GPU traffic inside the call.           */
+  int32_t want_ncomp;  /* compute n_compared_sites (the reference always does)                   */
+  int32_t want_trans;  /* fused transmission likelihood: needs days != NULL                      */
+  const int32_t *days; /* host: sampling day number per sample (days since any epoch)            */
+  double lamb, beta, threshold_Ek; /* trans_dist args (src/transcluster.hpp:241)                 */
+  int32_t sweep_variant; /* 0 = default kernel; others are tuning variants (bench only)          */
+  int32_t keep_on_device; /* reserved */
+} tracs_opts_t;
+
+/* Replaces TRACS.pairsnp(fasta, n_threads, dist, filter) -- src/python_bindings.cpp:12-13,
+ * src/pairsnp.hpp:320-458. paths: 1 or 2 FASTA(.gz) files (2 = query x db). n_threads sizes only
+ * host-side parsing. */
+int tracs_pairsnp(const char *const *paths, int n_paths, int n_threads, int32_t dist, int filter,
+                  tracs_edges_t *out);
+
+/* Same sweep on an alignment already held as an ASCII matrix seqs[n][pitch] (the bytes
+ * load_seqs keeps per record, src/pairsnp.hpp:99-110) in HOST memory; includes the H2D copy. */
+int tracs_pairsnp_host(const uint8_t *seqs, size_t n, size_t L, size_t pitch, const tracs_opts_t *opts,
+                       tracs_edges_t *out);
+
+/* Same, with the ASCII matrix already resident in DEVICE memory (pitch % 16 == 0). */
+int tracs_pairsnp_device(const uint8_t *dev_seqs, size_t n, size_t L, size_t pitch, const tracs_opts_t *opts,
+                         tracs_edges_t *out);
+
+void tracs_edges_free(tracs_edges_t *e);
+
+/* Replaces TRACS.trans_dist(snpdiff, datediff, lamb, beta, threshold_Ek) --
+ * src/python_bindings.cpp:19-21, src/transcluster.hpp:240-287. p0_log and eK: caller-allocated,
+ * n doubles each. */
+int tracs_trans_dist(const int32_t *snpdiff, const double *datediff, size_t n, double lamb, double beta,
+                     double threshold_Ek, double *p0_log, double *eK);
+
+/* Replaces TRACS.lprob_k_given_N(N, k, delta, lamb, beta, lgamma) -- src/python_bindings.cpp:15-17,
+ * src/transcluster.hpp:90-129. Scalar, test-only entry in the reference; host arithmetic.
+ * out[0] = lprob, out[1] = lhs. Fails (index error) if the table is shorter than N+k+2. */
+int tracs_lprob_k_given_N(size_t N, size_t k, double delta, double lamb, double beta, const double *lgamma_tab,
+                          size_t n_lgamma, double out[2]);
+
+/* Replaces TRACS.calculate_posteriors(counts, alphas, keep, threshold) --
+ * src/python_bindings.cpp:23-25, src/dmultinomial.hpp:8-86. Not on the hot path (align stage);
+ * exported so `import tracs.align` keeps working. Host arithmetic. out: rows*cols doubles. */
+int tracs_calculate_posteriors(const double *counts, size_t rows, size_t cols, const double *alphas, size_t n_alpha,
+                               int keep, double threshold, double *out);
+
+/* Min-over-references combine (tracs/distance.py:159-258 + tracs/cluster.py:104-113
+ * realise it implicitly): edges keyed by unordered (a,b) sample-id pair, value = min. Inputs are
+ * concatenated per-MSA edge lists with GLOBAL sample ids. Outputs caller-allocated (n each);
+ * *n_out receives the number of distinct pairs, sorted by (min id, max id). Runs on the device. */
+int tracs_min_over_refs(const uint64_t *a, const uint64_t *b, const double *val, size_t n, uint64_t *out_a,
+                        uint64_t *out_b, double *out_val, size_t *n_out);
+
+const char *tracs_last_error(void);
+int tracs_last_stats(tracs_stats_t *out);
+int tracs_device_count(void);
+int tracs_set_device(int device);
+
+/* ---- bench / test utilities (not in the reference) ------------------------------------------ */
+
+/* Seeded synthetic alignment generated directly in device memory (SURVEY 8d generator G).
+ * dev_seqs: device buffer n*pitch bytes. dev_days (optional, device, n int32): sampling days. */
+typedef struct tracs_synth {
+  uint64_t n, L, pitch, seed;
+  double p_var;    /* fraction of variable sites                         */
+  uint32_t n_clusters;
+  double mu;       /* mean private substitutions per sample              */
+  double p_N;      /* iid N probability per (sample, site)               */
+  double p_amb;    /* ambiguity-code probability per (sample, var site)  */
+  double gc;
+  uint32_t n_days; /* days drawn uniformly from [0, n_days)              */
+  uint32_t gaps;   /* number of '-' runs of length L/1000 per sample     */
+} tracs_synth_t;
+int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev_days);
+
+/* Device memory helpers so a host program can own device-resident inputs without a CUDA binding. */
+int tracs_dev_alloc(void **p, size_t bytes);
+int tracs_dev_free(void *p);
+int tracs_host_alloc_pinned(void **p, size_t bytes);
+int tracs_host_free_pinned(void *p);
+int tracs_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int tracs_memcpy_h2d(void *dst, const void *src, size_t bytes);
+
+/* Measures the INT-pipe peak on the current device with register-resident loops.
+ * out[0] = LOP3 warp-lane ops/s, out[1] = POPC ops/s, out[2] = IADD ops/s,
+ * out[3] = word-pairs/s of the (4 LOP3 + POPC + ADD) mix, out[4] = SM clock MHz seen (cycles/time). */
+int tracs_int_peak(double out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,137 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle, bit-exact for edges."""
+import os
+
+import numpy as np
+import pytest
+
+import tracs_b200
+from tracs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+IMAX = 2147483647
+
+
+def _cmp(res, orc):
+    r, c, d, f, nn = orc
+    assert res["rows"].tolist() == r.tolist()
+    assert res["cols"].tolist() == c.tolist()
+    assert res["dist"].tolist() == d.tolist()
+    assert res["ncomp"].tolist() == nn.tolist()
+
+
+@pytest.mark.parametrize("n,L,dist", [(2, 1, IMAX), (5, 31, IMAX), (7, 32, 3), (33, 33, IMAX), (128, 1000, 40), (129, 4097, 25),
+                                      (300, 20000, 30), (257, 1023, 0), (64, 5000, IMAX), (3, 70000, IMAX)])
+def test_matrix_parity(oracle_mod, n, L, dist):
+    s = synth.generate(n, L, p_var=0.05, n_clusters=4, mu=3, p_N=0.02, p_amb=0.05, seed=n * 7 + L, lowercase=0.05,
+                       odd_chars=0.01, three_base=True)
+    res = tracs_b200.pairsnp_matrix(s, dist=dist)
+    _cmp(res, oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4))
+
+
+def test_identical_and_allN(oracle_mod):
+    s = synth.generate(40, 500, p_var=0.0, p_N=0.0, gaps=0, seed=3)
+    s[7, :] = ord("N")
+    s[9, :] = ord("-")
+    res = tracs_b200.pairsnp_matrix(s, dist=0)
+    _cmp(res, oracle_mod.pairsnp_ascii(s, dist=0))
+    assert len(res["rows"]) == 40 * 39 // 2
+
+
+def test_negative_dist_and_empty(oracle_mod):
+    s = synth.generate(10, 100, p_var=0.3, seed=5)
+    res = tracs_b200.pairsnp_matrix(s, dist=-1)
+    assert len(res["rows"]) == 0
+
+
+def test_two_file_ranges(oracle_mod):
+    s = synth.generate(300, 3000, p_var=0.05, n_clusters=3, mu=4, p_N=0.01, p_amb=0.02, seed=11)
+    for n1 in (1, 100, 128, 299):
+        res = tracs_b200.pairsnp_matrix(s, dist=60, i_end=n1, j_start=n1)
+        _cmp(res, oracle_mod.pairsnp_ascii(s, i_end=n1, j_start=n1, dist=60, n_threads=4))
+
+
+def test_sharded_equals_single(oracle_mod):
+    s = synth.generate(700, 4000, p_var=0.05, n_clusters=5, mu=4, p_N=0.01, seed=12)
+    full = tracs_b200.pairsnp_matrix(s, dist=80)
+    for world in (2, 3, 8):
+        parts = [tracs_b200.pairsnp_matrix(s, dist=80, shard_rank=r, shard_world=world) for r in range(world)]
+        key = np.concatenate([(p["rows"] << np.uint64(32)) | p["cols"] for p in parts])
+        order = np.argsort(key, kind="stable")
+        for k in ("rows", "cols", "dist", "ncomp"):
+            assert np.concatenate([p[k] for p in parts])[order].tolist() == full[k].tolist()
+
+
+def test_fasta_entry_point(oracle_mod, tmp_path):
+    s = synth.generate(37, 2500, p_var=0.05, n_clusters=3, mu=3, p_N=0.02, p_amb=0.05, seed=21, lowercase=0.1, odd_chars=0.01)
+    for k, (gz, width, desc) in enumerate([(False, 0, False), (True, 60, True), (False, 7, True)]):
+        p = str(tmp_path / ("a%d.fa%s" % (k, ".gz" if gz else "")))
+        synth.write_fasta(p, s, width=width, descriptions=desc)
+        got = tracs_b200.pairsnp(fasta=[p], n_threads=2, dist=50, filter=False)
+        exp = oracle_mod.pairsnp([p], n_threads=2, dist=50)
+        assert isinstance(got[0], list) and isinstance(got[3], list)
+        for t in range(6):
+            assert got[t] == exp[t]
+    p1, p2 = str(tmp_path / "q.fa"), str(tmp_path / "db.fa.gz")
+    synth.write_fasta(p1, s[:10], names=["q%d" % i for i in range(10)])
+    synth.write_fasta(p2, s[10:], names=["d%d" % i for i in range(27)])
+    got = tracs_b200.pairsnp(fasta=[p1, p2], n_threads=1, dist=IMAX, filter=False)
+    exp = oracle_mod.pairsnp([p1, p2], dist=IMAX)
+    for t in range(6):
+        assert got[t] == exp[t]
+
+
+def test_fasta_errors(tmp_path):
+    p = str(tmp_path / "ragged.fa")
+    open(p, "w").write(">a\nACGT\n>b\nACG\n")
+    with pytest.raises(RuntimeError, match="variable sequence lengths"):
+        tracs_b200.pairsnp(fasta=[p], n_threads=1, dist=10, filter=False)
+    with pytest.raises(RuntimeError, match="Invalid number of fasta files"):
+        tracs_b200.pairsnp(fasta=[p, p, p], n_threads=1, dist=10, filter=False)
+
+
+def test_trans_dist_kat_and_grid(oracle_mod):
+    # reference tests/test_trans_distance.py:29-42 (delta = one day, CLI default rates)
+    d = 86400 / 31556952.0
+    p0, eK = tracs_b200.trans_dist(np.array([0, 2]), np.array([d, d]), 29.903, 73.0, 0.01)
+    assert abs(np.exp(p0[0]) - 0.23794988406662973) < 1e-6 and abs(np.exp(p0[1]) - 0.024467137572328577) < 1e-6
+    assert abs(eK[0] - 2.6335200453700187) < 1e-6 and abs(eK[1] - 7.315670110063259) < 1e-6
+    for lamb, beta in ((29.903, 73.0), (5.3, 6.0)):
+        for thr in (0.01, 1e-6):
+            N = np.repeat(np.arange(0, 41), 60).astype(np.int32)
+            days = np.tile(np.arange(0, 180, 3), 41)
+            dt = days * 86400.0 / 31556952.0
+            p0, eK = tracs_b200.trans_dist(N, dt, lamb, beta, thr)
+            op0, oeK, ke = oracle_mod.trans_dist(N, dt, lamb, beta, thr, with_k_exit=True)
+            p0, eK = np.array(p0), np.array(eK)
+            assert np.allclose(p0, op0, rtol=1e-6, atol=0)
+            dom = np.isfinite(oeK) & ((N + ke + 1 < 10000) | (dt == 0))
+            assert dom.sum() > 0.9 * dom.size
+            assert np.allclose(eK[dom], oeK[dom], rtol=1e-6, atol=0)
+
+
+def test_fused_trans(oracle_mod):
+    s = synth.generate(200, 3000, p_var=0.05, n_clusters=4, mu=3, p_N=0.01, seed=31)
+    days = np.random.default_rng(1).integers(0, 120, size=200).astype(np.int32)
+    res = tracs_b200.pairsnp_matrix(s, dist=30, days=days, lamb=29.903, beta=73.0, threshold_Ek=0.01)
+    r, c, d, f, nn = oracle_mod.pairsnp_ascii(s, dist=30)
+    assert res["rows"].tolist() == r.tolist() and res["dist"].tolist() == d.tolist()
+    dt = np.abs(days[r.astype(int)] * 86400.0 - days[c.astype(int)] * 86400.0) / 31556952.0
+    assert res["datediff"].tolist() == dt.tolist()
+    op0, oeK = oracle_mod.trans_dist(d.astype(np.int32), dt, 29.903, 73.0, 0.01)
+    assert np.allclose(res["p0_log"], op0, rtol=1e-6, atol=0)
+    assert np.allclose(res["eK"], oeK, rtol=1e-6, atol=0)
+
+
+def test_min_over_refs():
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 50, 5000).astype(np.uint64)
+    b = rng.integers(0, 50, 5000).astype(np.uint64)
+    v = rng.integers(0, 100, 5000).astype(np.float64)
+    oa, ob, ov = tracs_b200.min_over_refs(a, b, v)
+    exp = {}
+    for x, y, z in zip(a.tolist(), b.tolist(), v.tolist()):
+        k = (min(x, y), max(x, y))
+        exp[k] = min(exp.get(k, 1e300), z)
+    ks = sorted(exp)
+    assert list(zip(oa.tolist(), ob.tolist())) == ks
+    assert ov.tolist() == [exp[k] for k in ks]

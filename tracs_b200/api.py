@@ -1,0 +1,133 @@
+"""Host-side mirror of the reference's native interface for the pairwise-distance hot path.
+
+Same names, argument meaning and error behaviour as the pybind11 module `TRACS` of
+gtonkinhill/tracs (src/python_bindings.cpp:8-26); everything executes in libtracs_b200.so."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import INT32_MAX, Opts, Edges
+
+
+def pairsnp(fasta, n_threads, dist, filter):
+    """TRACS.pairsnp (src/python_bindings.cpp:12-13; src/pairsnp.hpp:320-458).
+
+    fasta: list of 1 or 2 FASTA(.gz) paths; returns the 6-tuple of Python lists
+    (rows, cols, distances, seq_names, filt_distances, n_compared_sites) in (row, col) order."""
+    fasta = [os.fspath(p) for p in fasta]
+    paths = (C.c_char_p * max(1, len(fasta)))(*[os.fsencode(p) for p in fasta])
+    e = Edges()
+    _lib.check(_lib.lib().tracs_pairsnp(paths, len(fasta), int(n_threads), int(dist), int(bool(filter)), C.byref(e)))
+    r = _lib.take_edges(e, as_lists=True)
+    return (r["rows"], r["cols"], r["dist"], r["names"], r["filt"], r["ncomp"])
+
+
+def trans_dist(snpdiff, datediff, lamb, beta, threshold_Ek):
+    """TRACS.trans_dist (src/python_bindings.cpp:19-21; src/transcluster.hpp:240-287).
+    Returns (log p0 list, E[K] list)."""
+    snp = np.ascontiguousarray(snpdiff, dtype=np.int32)
+    dt = np.ascontiguousarray(datediff, dtype=np.float64)
+    if snp.shape != dt.shape:
+        # the reference indexes datediff[i] for i < len(snpdiff) (src/transcluster.hpp:263-265)
+        raise IndexError("snpdiff and datediff must have the same length")
+    n = snp.size
+    p0 = np.empty(n, np.float64)
+    eK = np.empty(n, np.float64)
+    _lib.check(_lib.lib().tracs_trans_dist(snp.ctypes.data, dt.ctypes.data, n, float(lamb), float(beta), float(threshold_Ek),
+                                          p0.ctypes.data, eK.ctypes.data))
+    return p0.tolist(), eK.tolist()
+
+
+def lprob_k_given_N(N, k, delta, lamb, beta, lgamma):
+    """TRACS.lprob_k_given_N (src/python_bindings.cpp:15-17; src/transcluster.hpp:90-129)."""
+    lg = np.ascontiguousarray(lgamma, dtype=np.float64)
+    out = np.empty(2, np.float64)
+    _lib.check(_lib.lib().tracs_lprob_k_given_N(int(N), int(k), float(delta), float(lamb), float(beta), lg.ctypes.data, lg.size,
+                                               out.ctypes.data))
+    return float(out[0]), float(out[1])
+
+
+def calculate_posteriors(counts, alphas, keep, threshold):
+    """TRACS.calculate_posteriors (src/python_bindings.cpp:23-25; src/dmultinomial.hpp:8-86)."""
+    c = np.ascontiguousarray(counts, dtype=np.float64)
+    if c.ndim != 2:
+        raise RuntimeError("counts must be a 2-D array")
+    a = np.ascontiguousarray(alphas, dtype=np.float64)
+    out = np.empty_like(c)
+    _lib.check(_lib.lib().tracs_calculate_posteriors(c.ctypes.data, c.shape[0], c.shape[1], a.ctypes.data, a.size, int(bool(keep)),
+                                                    float(threshold), out.ctypes.data))
+    return out
+
+
+# ---- extras (not in the reference module) ------------------------------------------------------
+
+def make_opts(dist=INT32_MAX, i_end=0, j_start=0, shard_rank=0, shard_world=1, want_ncomp=True, days=None, lamb=29.903,
+              beta=73.0, threshold_Ek=0.01, filter=False):
+    o = Opts()
+    o.dist = int(dist)
+    o.filter = int(bool(filter))
+    o.i_end = int(i_end)
+    o.j_start = int(j_start)
+    o.shard_rank = int(shard_rank)
+    o.shard_world = int(shard_world)
+    o.want_ncomp = int(bool(want_ncomp))
+    keep = None
+    if days is not None:
+        keep = np.ascontiguousarray(days, dtype=np.int32)
+        o.days = keep.ctypes.data_as(C.POINTER(C.c_int32))
+        o.want_trans = 1
+    o.lamb, o.beta, o.threshold_Ek = float(lamb), float(beta), float(threshold_Ek)
+    return o, keep
+
+
+def pairsnp_matrix(seqs, **kw):
+    """Pair sweep on a HOST ASCII matrix uint8[n][L] (the bytes load_seqs holds per record);
+    H2D copy included. Returns a dict of numpy arrays (rows, cols, dist, ncomp[, p0_log, eK, datediff])."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    n, L = seqs.shape
+    o, keep = make_opts(**kw)
+    e = Edges()
+    _lib.check(_lib.lib().tracs_pairsnp_host(seqs.ctypes.data, n, L, L, C.byref(o), C.byref(e)))
+    return _lib.take_edges(e, names=False)
+
+
+def pairsnp_device(dev_ptr, n, L, pitch, **kw):
+    """Pair sweep on a DEVICE-resident ASCII matrix (raw device pointer as int)."""
+    o, keep = make_opts(**kw)
+    e = Edges()
+    _lib.check(_lib.lib().tracs_pairsnp_device(C.c_void_p(dev_ptr), n, L, pitch, C.byref(o), C.byref(e)))
+    return _lib.take_edges(e, names=False)
+
+
+def min_over_refs(a, b, val):
+    """Min-over-references combine: unordered (a,b) -> min(val). Sorted by (lo, hi)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    v = np.ascontiguousarray(val, dtype=np.float64)
+    n = a.size
+    oa = np.empty(n, np.uint64)
+    ob = np.empty(n, np.uint64)
+    ov = np.empty(n, np.float64)
+    m = C.c_size_t(0)
+    _lib.check(_lib.lib().tracs_min_over_refs(a.ctypes.data, b.ctypes.data, v.ctypes.data, n, oa.ctypes.data, ob.ctypes.data,
+                                             ov.ctypes.data, C.byref(m)))
+    return oa[:m.value].copy(), ob[:m.value].copy(), ov[:m.value].copy()
+
+
+def synth_device(dev_ptr, n, L, pitch, seed=1, p_var=0.01, n_clusters=20, mu=5.0, p_N=1e-3, p_amb=0.0, gc=0.5, n_days=180,
+                 gaps=2, dev_days=None):
+    cfg = _lib.Synth(n, L, pitch, seed, p_var, n_clusters, mu, p_N, p_amb, gc, n_days, gaps)
+    _lib.check(_lib.lib().tracs_synth_device(C.byref(cfg), C.c_void_p(dev_ptr), C.c_void_p(dev_days) if dev_days else None))
+
+
+def int_peak():
+    out = np.zeros(8, np.float64)
+    _lib.check(_lib.lib().tracs_int_peak(out.ctypes.data))
+    return {"lop3_per_s": out[0], "popc_per_s": out[1], "iadd_per_s": out[2], "mix_wordpairs_per_s": out[3],
+            "sm_mhz_lop3": out[4], "n_sm": int(out[5]), "sm_mhz_mix": out[6]}
+
+
+def last_stats():
+    return _lib.last_stats()

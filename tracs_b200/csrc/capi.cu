@@ -1,0 +1,524 @@
+// C ABI of libtracs_b200.so (see include/tracs_b200.h for the contract and reference citations).
+#include <cub/cub.cuh>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <numeric>
+#include <stdexcept>
+
+#include "common.cuh"
+
+namespace tracs {
+
+thread_local std::string g_err;
+thread_local tracs_stats_t g_stats;
+void set_error(const std::string &msg) { g_err = msg; }
+
+static void require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw std::runtime_error(std::string("tracs_b200: no CUDA device available (") + cudaGetErrorString(e) +
+                             "); this library has no CPU fallback");
+}
+
+template <typename F>
+static int guarded(F &&f) {
+  try {
+    f();
+    return 0;
+  } catch (const CudaError &e) {
+    set_error(e.msg);
+    cudaGetLastError();
+    return 2;
+  } catch (const std::out_of_range &e) {
+    set_error(e.what());
+    return 3;
+  } catch (const std::exception &e) {
+    set_error(e.what());
+    return 1;
+  }
+}
+
+template <typename T>
+static T *dup_array(const std::vector<T> &v) {
+  T *p = (T *)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+  if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+  return p;
+}
+
+static void finish_edges(HostEdges &he, const tracs_opts_t &o, uint64_t n, uint64_t L, tracs_edges_t *out,
+                         cudaStream_t st) {
+  const size_t E = he.rows.size();
+  out->n_edges = E;
+  out->rows = dup_array(he.rows);
+  out->cols = dup_array(he.cols);
+  out->dist = dup_array(he.dist);
+  out->ncomp = dup_array(he.ncomp);
+  out->filt = (uint64_t *)calloc(std::max<size_t>(1, E), sizeof(uint64_t));
+  out->seq_length = L;
+  if (o.want_trans && o.days) {
+    // tracs/transcluster.py:26-36: seconds since epoch -> |dt| / SECONDS_IN_YEAR -> trans_dist
+    std::vector<double> dt(E), p0(E), ek(E);
+    std::vector<int32_t> d32(E);
+    for (size_t e = 0; e < E; ++e) {
+      const double ti = (double)o.days[he.rows[e]] * 86400.0, tj = (double)o.days[he.cols[e]] * 86400.0;
+      dt[e] = fabs(ti - tj) / 31556952.0;
+      d32[e] = (int32_t)he.dist[e];
+    }
+    trans_dist_device(d32.data(), dt.data(), E, o.lamb, o.beta, o.threshold_Ek, p0.data(), ek.data(), st);
+    out->p0_log = dup_array(p0);
+    out->eK = dup_array(ek);
+    out->datediff = dup_array(dt);
+  }
+  (void)n;
+}
+
+// ---- synthetic alignment generator (generator G; hash-based, seeded) ---------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+struct SynthDev {
+  uint64_t n, L, pitch, seed;
+  uint32_t thr_var24, thr_found16, thr_gc16, n_clusters;
+  uint32_t thr_priv32, thr_N32, thr_amb16, n_days, gaps;
+  uint64_t gap_len;
+};
+__global__ void k_synth(SynthDev c, uint8_t *__restrict__ seqs) {
+  const uint64_t chunks = c.pitch / 16;
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= c.n * chunks) return;
+  const uint64_t s = gid / chunks, ch = gid % chunks;
+  const uint32_t cluster = (uint32_t)(mix64(c.seed * 0x100000001b3ull + 0x51ull + s) % c.n_clusters);
+  uint64_t g0[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  for (uint32_t r = 0; r < c.gaps && r < 4; ++r)
+    if (c.L > c.gap_len) g0[r] = mix64(c.seed ^ (0xabcdefull + s * 8 + r)) % (c.L - c.gap_len);
+  const char B[4] = {'A', 'C', 'G', 'T'};
+  // 2-base IUPAC codes indexed [b][o]
+  const char AMB[4][4] = {{'A', 'M', 'R', 'W'}, {'M', 'C', 'S', 'Y'}, {'R', 'S', 'G', 'K'}, {'W', 'Y', 'K', 'T'}};
+  uint32_t outw[4];
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w = 0;
+    for (int t = 0; t < 4; ++t) {
+      const uint64_t site = ch * 16 + q * 4 + t;
+      char chv = 'N';
+      if (site < c.L) {
+        const uint64_t hs = mix64(c.seed * 0x9E3779B97F4A7C15ull + site);
+        uint32_t b;
+        if ((hs & 0xFFFFu) < c.thr_gc16) b = ((hs >> 60) & 1) ? 1u : 2u; else b = ((hs >> 60) & 1) ? 0u : 3u;
+        const bool isvar = ((hs >> 16) & 0xFFFFFFu) < c.thr_var24;
+        bool amb = false;
+        uint32_t other = 0;
+        if (isvar) {
+          const uint64_t hc = mix64(hs ^ ((uint64_t)(cluster + 1) * 0xD6E8FEB86659FD93ull));
+          if ((hc & 0xFFFFu) < c.thr_found16) b = (b + 1 + (uint32_t)((hc >> 16) % 3)) & 3u;
+          const uint64_t hp = mix64(hs ^ ((s + 1) * 0xA24BAED4963EE407ull));
+          if ((uint32_t)hp < c.thr_priv32) b = (b + 1 + (uint32_t)((hp >> 32) % 3)) & 3u;
+          if (((hp >> 40) & 0xFFFFu) < c.thr_amb16) { amb = true; other = (b + 1 + (uint32_t)((hp >> 56) % 3)) & 3u; }
+        }
+        chv = amb ? AMB[b][other] : B[b];
+        const uint64_t hn = mix64((c.seed + 0x7777ull) * 0xC2B2AE3D27D4EB4Full + s * c.L + site);
+        if ((uint32_t)hn < c.thr_N32) chv = 'N';
+        for (int r = 0; r < 4; ++r) if (site >= g0[r] && site - g0[r] < c.gap_len) chv = '-';
+      }
+      w |= (uint32_t)(uint8_t)chv << (8 * t);
+    }
+    outw[q] = w;
+  }
+  *reinterpret_cast<uint4 *>(seqs + s * c.pitch + ch * 16) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+}
+__global__ void k_synth_days(uint64_t n, uint64_t seed, uint32_t n_days, int32_t *days) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) days[s] = (int32_t)(mix64(seed * 31ull + 0xDA7Eull + s) % (n_days ? n_days : 1));
+}
+
+// ---- INT pipe peak micro-benchmarks -------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_peak(uint32_t *out, int iters, long long *cycles) {
+  uint32_t x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+  uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {  // LOP3 only: 16 independent chains
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[(i + 1) & 15]), "r"(x[(i + 5) & 15]));
+    } else if (MODE == 1) {  // POPC only
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("popc.b32 %0, %0;" : "+r"(x[i]));
+    } else if (MODE == 2) {  // IADD only
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(x[(i + 3) & 15]));
+    } else {  // sweep mix on register operands: 2 row x 2 col uint4, 4 word-pairs x 4 repeats
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t m;
+            asm volatile("and.b32 %0, %1, %2;" : "=r"(m) : "r"(x[i * 4 + 0]), "r"(x[8 + j * 4 + 0]));
+            asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 1]), "r"(x[8 + j * 4 + 1]));
+            asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 2]), "r"(x[8 + j * 4 + 2]));
+            asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 3]), "r"(x[8 + j * 4 + 3]));
+            uint32_t p;
+            asm volatile("popc.b32 %0, %1;" : "=r"(p) : "r"(m));
+            acc[(i * 2 + j) + 4 * (r & 1)] += p;
+          }
+        x[r] += acc[r];  // keep operands changing so nothing hoists
+      }
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s ^= x[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+}  // namespace tracs
+
+using namespace tracs;
+
+extern "C" {
+
+const char *tracs_last_error(void) { return g_err.c_str(); }
+
+int tracs_last_stats(tracs_stats_t *out) {
+  *out = g_stats;
+  return 0;
+}
+
+int tracs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int tracs_set_device(int device) {
+  return guarded([&] { TRACS_CK(cudaSetDevice(device)); });
+}
+
+void tracs_edges_free(tracs_edges_t *e) {
+  if (!e) return;
+  free(e->rows); free(e->cols); free(e->dist); free(e->filt); free(e->ncomp);
+  free(e->p0_log); free(e->eK); free(e->datediff);
+  if (e->names) {
+    for (size_t i = 0; i < e->n_names; ++i) free(e->names[i]);
+    free(e->names);
+  }
+  memset(e, 0, sizeof *e);
+}
+
+static tracs_opts_t normalise(const tracs_opts_t *opts, size_t n) {
+  tracs_opts_t o;
+  if (opts) o = *opts; else { memset(&o, 0, sizeof o); o.dist = INT32_MAX; o.want_ncomp = 1; }
+  if (o.i_end == 0 || o.i_end > n) o.i_end = n;
+  if (o.shard_world <= 0) { o.shard_world = 1; o.shard_rank = 0; }
+  return o;
+}
+
+int tracs_pairsnp_device(const uint8_t *dev_seqs, size_t n, size_t L, size_t pitch, const tracs_opts_t *opts,
+                         tracs_edges_t *out) {
+  memset(out, 0, sizeof *out);
+  memset(&g_stats, 0, sizeof g_stats);
+  return guarded([&] {
+    require_device();
+    tracs_opts_t o = normalise(opts, n);
+    if (o.filter) throw std::runtime_error("tracs_b200: filter=True (recombination filter) is not implemented yet");
+    HostEdges he;
+    sweep_device(dev_seqs, n, L, pitch, o, he, 0);
+    finish_edges(he, o, n, L, out, 0);
+  });
+}
+
+int tracs_pairsnp_host(const uint8_t *seqs, size_t n, size_t L, size_t pitch, const tracs_opts_t *opts,
+                       tracs_edges_t *out) {
+  memset(out, 0, sizeof *out);
+  memset(&g_stats, 0, sizeof g_stats);
+  return guarded([&] {
+    require_device();
+    tracs_opts_t o = normalise(opts, n);
+    if (o.filter) throw std::runtime_error("tracs_b200: filter=True (recombination filter) is not implemented yet");
+    HostEdges he;
+    if (n > 0) {
+      const size_t dp = std::max<size_t>(32, (L + 31) / 32 * 32);
+      DevBuf<uint8_t> d(n * dp);
+      if (dp != L) TRACS_CK(cudaMemsetAsync(d.p, 'N', n * dp, 0));
+      if (L > 0) TRACS_CK(cudaMemcpy2DAsync(d.p, dp, seqs, pitch, L, n, cudaMemcpyHostToDevice, 0));
+      sweep_device(d.p, n, L, dp, o, he, 0);
+      g_stats.h2d_bytes += (uint64_t)n * L;
+    }
+    finish_edges(he, o, n, L, out, 0);
+  });
+}
+
+int tracs_pairsnp(const char *const *paths, int n_paths, int n_threads, int32_t dist, int filter,
+                  tracs_edges_t *out) {
+  memset(out, 0, sizeof *out);
+  memset(&g_stats, 0, sizeof g_stats);
+  return guarded([&] {
+    // src/pairsnp.hpp:340-343
+    if (n_paths < 1 || n_paths > 2) throw std::runtime_error("Invalid number of fasta files!");
+    require_device();
+    std::vector<uint8_t> ascii;
+    std::vector<std::string> names;
+    uint64_t L = 0, L2 = 0;
+    const uint64_t n1 = read_fasta(paths[0], n_threads, ascii, names, L);
+    uint64_t n = n1;
+    tracs_opts_t o;
+    memset(&o, 0, sizeof o);
+    o.dist = dist; o.filter = filter; o.want_ncomp = 1; o.i_end = n1; o.j_start = 0;
+    if (n_paths == 2) {
+      L2 = L;
+      const uint64_t n2 = read_fasta(paths[1], n_threads, ascii, names, L2);
+      // the reference does not cross-check the files (bitsets of unequal size: undefined); refuse
+      if (n2 > 0 && n1 > 0 && L2 != L) throw std::runtime_error("Error reading FASTA, variable sequence lengths!");
+      if (n1 == 0) L = L2;
+      n += n2;
+      o.j_start = n1;
+    }
+    tracs_edges_t tmp;
+    const int rc = (n1 == 0 || o.j_start >= n) ? 0 : tracs_pairsnp_host(ascii.data(), n, L, L, &o, &tmp);
+    if (n1 == 0 || o.j_start >= n) {
+      memset(&tmp, 0, sizeof tmp);
+      tmp.rows = (uint64_t *)calloc(1, 8); tmp.cols = (uint64_t *)calloc(1, 8); tmp.dist = (uint64_t *)calloc(1, 8);
+      tmp.filt = (uint64_t *)calloc(1, 8); tmp.ncomp = (uint64_t *)calloc(1, 8);
+      tmp.seq_length = L;
+    }
+    if (rc) throw std::runtime_error(g_err);
+    *out = tmp;
+    out->n_names = names.size();
+    out->names = (char **)malloc(std::max<size_t>(1, names.size()) * sizeof(char *));
+    for (size_t i = 0; i < names.size(); ++i) out->names[i] = strdup(names[i].c_str());
+  });
+}
+
+int tracs_trans_dist(const int32_t *snpdiff, const double *datediff, size_t n, double lamb, double beta,
+                     double threshold_Ek, double *p0_log, double *eK) {
+  return guarded([&] {
+    require_device();
+    trans_dist_device(snpdiff, datediff, n, lamb, beta, threshold_Ek, p0_log, eK, 0);
+  });
+}
+
+// src/transcluster.hpp:62-75 (host copy for the scalar, test-only entry point)
+static double lae_host(double x, double y) {
+  const double t = x - y;
+  if (x == y) return x + M_LN2;
+  if (t > 0) return x + log1p(exp(-t));
+  else if (t <= 0) return y + log1p(exp(t));
+  return t;
+}
+
+int tracs_lprob_k_given_N(size_t N, size_t k, double delta, double lamb, double beta, const double *lg,
+                          size_t n_lg, double out[2]) {
+  return guarded([&] {
+    if (n_lg < N + k + 2) throw std::out_of_range("lgamma table shorter than N + k + 2");
+    // src/transcluster.hpp:90-129. The binomial-coefficient terms lg[i+1] cancel inside the
+    // integral sum; they are kept out here and the remaining factor lg[N+k+1]-lg[N+1] hoisted.
+    double lprob, lhs;
+    const double M = (double)(N + k);
+    if (delta > 0) {
+      lprob = (double)(N + 1) * log(lamb) - delta * (lamb + beta) + (double)k * log(beta) - lg[k + 1];
+      double pois = -INFINITY;
+      const double lld = log(lamb * delta);
+      for (size_t i = 0; i <= N; ++i) pois = lae_host((double)i * lld - lg[i + 1], pois);
+      pois -= lamb * delta;
+      lprob -= pois;
+      double integ = -INFINITY;
+      const double ld = log(delta), llb = log(lamb + beta);
+      for (size_t i = 0; i <= N + k; ++i)
+        integ = lae_host(lg[N + k + 1] - lg[N + k - i + 1] + (M - (double)i) * ld - (double)(i + 1) * llb, integ);
+      integ -= lg[N + 1];
+      lhs = lprob;
+      lprob += integ;
+    } else {
+      lprob = (double)(N + 1) * log(lamb) + (double)k * log(beta) + lg[N + k + 1] - lg[N + 1] - lg[k + 1] -
+              (M + 1.0) * log(lamb + beta);
+      lhs = lprob;
+    }
+    out[0] = lprob;
+    out[1] = lhs;
+  });
+}
+
+// src/dmultinomial.hpp:8-86 -- align-stage helper kept for import compatibility (host arithmetic).
+int tracs_calculate_posteriors(const double *counts, size_t rows, size_t cols, const double *alphas_in,
+                               size_t n_alpha, int keep, double threshold, double *out) {
+  return guarded([&] {
+    if (n_alpha == 0) throw std::runtime_error("alphas must not be empty");
+    if (n_alpha < cols) throw std::out_of_range("need at least one alpha per column");
+    std::vector<double> alphas(alphas_in, alphas_in + n_alpha);
+    std::sort(alphas.begin(), alphas.end(), std::greater<double>());
+    const double a0 = std::accumulate(alphas.begin(), alphas.end(), 0.0);
+    const double a_min = alphas[0] / a0;
+    std::vector<size_t> order(cols);
+    for (size_t r = 0; r < rows; ++r) {
+      const double *row = counts + r * cols;
+      double *res = out + r * cols;
+      double total = 0;
+      for (size_t c = 0; c < cols; ++c) total += row[c];
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return row[x] > row[y]; });
+      if (total <= 0) {
+        for (size_t c = 0; c < cols; ++c) res[c] = a_min;
+      } else {
+        // ties share one alpha: the rank only advances when the sorted count changes
+        size_t rank = 0;
+        for (size_t c = 0; c < cols; ++c) {
+          const size_t id = order[c];
+          res[id] = (row[id] + alphas[rank]) / (total + a0);
+          if (c + 1 < cols && row[id] != row[order[c + 1]]) rank++;
+        }
+      }
+      for (size_t c = 0; c < cols; ++c)
+        if (res[c] <= threshold) res[c] = (keep && row[c] > 0) ? threshold : 0.0;
+    }
+  });
+}
+
+int tracs_min_over_refs(const uint64_t *a, const uint64_t *b, const double *val, size_t n, uint64_t *out_a,
+                        uint64_t *out_b, double *out_val, size_t *n_out) {
+  return guarded([&] {
+    require_device();
+    *n_out = 0;
+    if (n == 0) return;
+    std::vector<uint64_t> keys(n);
+    for (size_t i = 0; i < n; ++i) {
+      const uint64_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
+      if (hi >= (1ull << 32)) throw std::runtime_error("sample id out of range");
+      keys[i] = (lo << 32) | hi;
+    }
+    DevBuf<uint64_t> k1(n), k2(n), ku(n);
+    DevBuf<double> v1(n), v2(n), vu(n);
+    DevBuf<uint64_t> d_runs(1);
+    TRACS_CK(cudaMemcpy(k1.p, keys.data(), n * 8, cudaMemcpyHostToDevice));
+    TRACS_CK(cudaMemcpy(v1.p, val, n * 8, cudaMemcpyHostToDevice));
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k1.p, k2.p, v1.p, v2.p, (int64_t)n);
+    cub::DeviceReduce::ReduceByKey(nullptr, tb2, k2.p, ku.p, v2.p, vu.p, d_runs.p, cub::Min(), (int64_t)n);
+    DevBuf<uint8_t> tmp(std::max(tb, tb2));
+    cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1.p, k2.p, v1.p, v2.p, (int64_t)n);
+    cub::DeviceReduce::ReduceByKey(tmp.p, tb2, k2.p, ku.p, v2.p, vu.p, d_runs.p, cub::Min(), (int64_t)n);
+    uint64_t runs = 0;
+    TRACS_CK(cudaMemcpy(&runs, d_runs.p, 8, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> hk(runs);
+    TRACS_CK(cudaMemcpy(hk.data(), ku.p, runs * 8, cudaMemcpyDeviceToHost));
+    TRACS_CK(cudaMemcpy(out_val, vu.p, runs * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < runs; ++i) {
+      out_a[i] = hk[i] >> 32;
+      out_b[i] = hk[i] & 0xFFFFFFFFull;
+    }
+    *n_out = runs;
+  });
+}
+
+int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev_days) {
+  return guarded([&] {
+    require_device();
+    if (cfg->pitch % 16 != 0 || cfg->pitch < cfg->L) throw std::runtime_error("synth: pitch must be a multiple of 16 and >= L");
+    SynthDev c;
+    c.n = cfg->n; c.L = cfg->L; c.pitch = cfg->pitch; c.seed = cfg->seed;
+    auto clamp01 = [](double x) { return x < 0 ? 0.0 : (x > 1 ? 1.0 : x); };
+    c.thr_var24 = (uint32_t)(clamp01(cfg->p_var) * 16777216.0);
+    c.thr_found16 = (uint32_t)(0.3 * 65536.0);
+    c.thr_gc16 = (uint32_t)(clamp01(cfg->gc) * 65536.0);
+    c.n_clusters = std::max(1u, cfg->n_clusters);
+    const double v = std::max(1.0, cfg->p_var * (double)cfg->L);
+    c.thr_priv32 = (uint32_t)std::min(4294967295.0, clamp01(cfg->mu / v) * 4294967296.0);
+    c.thr_N32 = (uint32_t)std::min(4294967295.0, clamp01(cfg->p_N) * 4294967296.0);
+    c.thr_amb16 = (uint32_t)(clamp01(cfg->p_amb) * 65536.0);
+    c.n_days = cfg->n_days; c.gaps = cfg->gaps;
+    c.gap_len = cfg->L / 1000;
+    const uint64_t total = c.n * (c.pitch / 16);
+    if (total) {
+      k_synth<<<(unsigned)((total + 255) / 256), 256>>>(c, dev_seqs);
+      TRACS_CK(cudaGetLastError());
+    }
+    if (dev_days && c.n) k_synth_days<<<(unsigned)((c.n + 255) / 256), 256>>>(c.n, c.seed, c.n_days, dev_days);
+    TRACS_CK(cudaDeviceSynchronize());
+  });
+}
+
+int tracs_dev_alloc(void **p, size_t bytes) {
+  return guarded([&] { require_device(); TRACS_CK(cudaMalloc(p, bytes)); });
+}
+int tracs_dev_free(void *p) {
+  return guarded([&] { TRACS_CK(cudaFree(p)); });
+}
+int tracs_host_alloc_pinned(void **p, size_t bytes) {
+  return guarded([&] { require_device(); TRACS_CK(cudaMallocHost(p, bytes)); });
+}
+int tracs_host_free_pinned(void *p) {
+  return guarded([&] { TRACS_CK(cudaFreeHost(p)); });
+}
+int tracs_memcpy_d2h(void *dst, const void *src, size_t bytes) {
+  return guarded([&] { TRACS_CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); });
+}
+int tracs_memcpy_h2d(void *dst, const void *src, size_t bytes) {
+  return guarded([&] { TRACS_CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); });
+}
+
+int tracs_int_peak(double out[8]) {
+  return guarded([&] {
+    require_device();
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = n_sm * 8, threads = 256, iters = 4096;
+    DevBuf<uint32_t> sink((size_t)blocks * threads);
+    DevBuf<long long> cyc(1);
+    Timer T(0);
+    auto run = [&](int mode) -> std::pair<double, double> {
+      float best = 1e30f;
+      long long cycles = 0;
+      for (int rep = 0; rep < 4; ++rep) {
+        T.start();
+        switch (mode) {
+          case 0: k_peak<0><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
+          case 1: k_peak<1><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
+          case 2: k_peak<2><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
+          default: k_peak<3><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
+        }
+        float ms = T.stop();
+        TRACS_CK(cudaGetLastError());
+        if (rep > 0 && ms < best) best = ms;
+      }
+      TRACS_CK(cudaMemcpy(&cycles, cyc.p, 8, cudaMemcpyDeviceToHost));
+      return {(double)best * 1e-3, (double)cycles};
+    };
+    const double lanes = (double)blocks * threads * iters;
+    auto r0 = run(0), r1 = run(1), r2 = run(2), r3 = run(3);
+    out[0] = lanes * 64 / r0.first;
+    out[1] = lanes * 64 / r1.first;
+    out[2] = lanes * 64 / r2.first;
+    out[3] = lanes * 16 / r3.first;  // word-pairs / s
+    // one CTA's clock64 span over the kernel's wall time ~ SM clock (CTAs run in 1+ waves: 8/SM resident)
+    out[4] = r0.second / r0.first / 1e6;
+    out[5] = (double)n_sm;
+    out[6] = r3.second / r3.first / 1e6;
+    out[7] = 0;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Shared declarations for libtracs_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/tracs_b200.h"
+
+namespace tracs {
+
+void set_error(const std::string &msg);
+extern thread_local tracs_stats_t g_stats;
+
+struct CudaError {
+  std::string msg;
+};
+
+#define TRACS_CK(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      char b__[512];                                                                               \
+      snprintf(b__, sizeof b__, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__,     \
+               __LINE__, cudaGetErrorString(e__));                                                 \
+      throw tracs::CudaError{b__};                                                                 \
+    }                                                                                              \
+  } while (0)
+
+// RAII device buffer
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) TRACS_CK(cudaMalloc((void **)&p, count * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+struct Timer {
+  cudaEvent_t a, b;
+  cudaStream_t s;
+  explicit Timer(cudaStream_t st) : s(st) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~Timer() {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+  void start() { cudaEventRecord(a, s); }
+  float stop() {
+    cudaEventRecord(b, s);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+  }
+};
+
+// ---- geometry of the pair sweep ------------------------------------------------------------
+constexpr int TILE = 128;  // samples per tile side
+constexpr int KC = 8;      // 32-site words per pipeline stage
+constexpr int STAGES = 3;  // shared-memory ring depth
+
+// FASTA reader (fasta.cpp): kseq-compatible record semantics (reference src/kseq.h:170-208).
+struct Alignment {
+  std::vector<uint8_t> ascii;  // n * L bytes, row-major, pitch == L
+  std::vector<std::string> names;
+  uint64_t n = 0, L = 0;
+};
+// appends the records of `path`; returns number of records read; throws std::runtime_error
+uint64_t read_fasta(const char *path, int n_threads, std::vector<uint8_t> &ascii, std::vector<std::string> &names,
+                    uint64_t &L);
+
+// host-side edge columns produced by the sweep (sorted by (row, col))
+struct HostEdges {
+  std::vector<uint64_t> rows, cols, dist, ncomp;
+};
+void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,
+                  HostEdges &out, cudaStream_t st);
+
+// transcluster on device (trans.cu)
+void trans_dist_device(const int32_t *snp, const double *dt, size_t n, double lamb, double beta, double thr,
+                       double *p0_log, double *eK, cudaStream_t st);
+
+}  // namespace tracs

@@ -1,0 +1,636 @@
+// Pair sweep for sm_100a: ASCII alignment (device) -> sparse edge list.
+//
+//   K0a k_pack      ASCII -> per-site AND of the 4-bit base masks over all samples (column mask),
+//                   full-length N bit-plane + its block summary        [HBM-bound, reads n*L bytes]
+//   K0b k_gather    variable sites only -> interleaved A/C/G/T bit-planes P[word][sample] (uint4)
+//   K1  k_sweep     128x128 pair tiles, bulk-async (TMA engine, UBLKCP) staged panels, 8x8 register
+//                   micro-tiles, LOP3 + POPC, fused threshold + edge append  [INT-pipe bound]
+//   K2  k_ncomp     compared-site count for emitted edges via block-sparse N-plane intersection
+//
+// Semantics restated from the reference (paths relative to gtonkinhill/tracs):
+//   base masks       src/pairsnp.hpp:107-199      d(i,j)   src/pairsnp.hpp:398-403
+//   threshold/emit   src/pairsnp.hpp:405-410      nn(i,j)  src/pairsnp.hpp:417-419
+//   pair range       src/pairsnp.hpp:352-360,395  order    src/pairsnp.hpp:450-457
+// Dropping a site whose column AND is non-zero (some base shared by every sample) changes no
+// d(i,j): such a site is a match for every pair.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <stdexcept>
+
+#include "common.cuh"
+
+namespace tracs {
+
+// ------------------------------------------------------------------------------------------
+// base-mask table: bit0=A bit1=C bit2=G bit3=T ; everything that is not an IUPAC code = 15
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t base_mask(uint32_t c) {
+  c &= 0xFFu;
+  if (c >= 'a' && c <= 'z') c -= 32;
+  switch (c) {
+    case 'A': return 1;
+    case 'C': return 2;
+    case 'G': return 4;
+    case 'T': return 8;
+    case 'M': return 3;
+    case 'R': return 5;
+    case 'W': return 9;
+    case 'S': return 6;
+    case 'Y': return 10;
+    case 'K': return 12;
+    case 'V': return 7;
+    case 'H': return 11;
+    case 'D': return 13;
+    case 'B': return 14;
+    default: return 15;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K0a: pack
+//   thread <-> one 32-site word (32 ASCII bytes) ; loops over a chunk of samples
+//   lut: 256 entries x 32 lanes (lane-private bank => conflict-free byte lookups)
+// ------------------------------------------------------------------------------------------
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_SCHUNK = 256;
+
+__device__ __forceinline__ uint32_t lut4(const uint32_t *lut_lane, uint32_t w) {
+  uint32_t e0 = lut_lane[(w & 0xFFu) << 5];
+  uint32_t e1 = lut_lane[((w >> 8) & 0xFFu) << 5];
+  uint32_t e2 = lut_lane[((w >> 16) & 0xFFu) << 5];
+  uint32_t e3 = lut_lane[(w >> 24) << 5];
+  return e0 | (e1 << 4) | (e2 << 8) | (e3 << 12);
+}
+// bit i of result = nibble i of x is 0xF
+__device__ __forceinline__ uint32_t nibbles_all_ones(uint32_t x) {
+  uint32_t t = x & (x >> 1);
+  t &= (t >> 2);
+  t &= 0x11111111u;
+  t = (t | (t >> 3)) & 0x03030303u;
+  t = (t | (t >> 6)) & 0x000F000Fu;
+  t = (t | (t >> 12)) & 0xFFu;
+  return t;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
+       uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/) {
+  __shared__ uint32_t lut[256 * 32];
+  for (int i = threadIdx.x; i < 256 * 32; i += PACK_THREADS) lut[i] = base_mask(i >> 5);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t *lut_lane = lut + lane;
+  const uint64_t w = (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x;  // word index
+  const uint64_t s0 = (uint64_t)blockIdx.y * PACK_SCHUNK;
+  const uint64_t s1 = min(n, s0 + PACK_SCHUNK);
+  const uint64_t site0 = w * 32;
+  // npitch is a multiple of 32 words, so a whole warp is either inside or outside the N-plane row
+  const bool in_row = w < npitch;
+  const bool has_sites = site0 < L;
+  uint32_t acc0 = ~0u, acc1 = ~0u, acc2 = ~0u, acc3 = ~0u;
+  uint32_t valid = 0xFFFFFFFFu;
+  if (has_sites && L - site0 < 32) valid = (1u << (uint32_t)(L - site0)) - 1u;
+  for (uint64_t s = s0; s < s1; ++s) {
+    uint32_t isn = 0;
+    if (has_sites) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(seqs + s * pitch + site0);
+      uint4 a = __ldg(src), b = __ldg(src + 1);
+      uint32_t m0 = lut4(lut_lane, a.x) | (lut4(lut_lane, a.y) << 16);
+      uint32_t m1 = lut4(lut_lane, a.z) | (lut4(lut_lane, a.w) << 16);
+      uint32_t m2 = lut4(lut_lane, b.x) | (lut4(lut_lane, b.y) << 16);
+      uint32_t m3 = lut4(lut_lane, b.z) | (lut4(lut_lane, b.w) << 16);
+      isn = nibbles_all_ones(m0) | (nibbles_all_ones(m1) << 8) | (nibbles_all_ones(m2) << 16) |
+            (nibbles_all_ones(m3) << 24);
+      isn &= valid;
+      acc0 &= m0; acc1 &= m1; acc2 &= m2; acc3 &= m3;
+    }
+    if (in_row) {
+      nplane[s * npitch + w] = isn;
+      // block summary: one bit per 4 words (128 sites), one byte per warp (1024 sites)
+      uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
+      if (lane == 0) {
+        uint32_t t = nz | (nz >> 1);
+        t |= (t >> 2);
+        t &= 0x11111111u;
+        nsum[s * spitch + (w >> 5)] = (uint8_t)nibbles_all_ones(t * 0xFu);
+      }
+    }
+  }
+  if (has_sites) {
+    // sites >= L in the last word must not look variable: force their nibbles non-zero
+    if (valid != 0xFFFFFFFFu) {
+      uint32_t nv = __popc(valid);
+      auto fix = [&](uint32_t &acc, uint32_t g) {
+        uint32_t v = nv > g * 8 ? min(8u, nv - g * 8) : 0u;
+        if (v < 8) acc |= (v == 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (4 * v)));
+      };
+      fix(acc0, 0); fix(acc1, 1); fix(acc2, 2); fix(acc3, 3);
+    }
+    uint32_t *cm = colmask + w * 4;
+    if (acc0 != ~0u) atomicAnd(cm + 0, acc0);
+    if (acc1 != ~0u) atomicAnd(cm + 1, acc1);
+    if (acc2 != ~0u) atomicAnd(cm + 2, acc2);
+    if (acc3 != ~0u) atomicAnd(cm + 3, acc3);
+  }
+}
+
+// per-sample N count: one CTA per sample
+__global__ void k_ncount(const uint32_t *__restrict__ nplane, uint64_t npitch, uint32_t *__restrict__ ncount) {
+  const uint64_t s = blockIdx.x;
+  const uint4 *row = reinterpret_cast<const uint4 *>(nplane + s * npitch);
+  uint32_t c = 0;
+  for (uint64_t i = threadIdx.x; i < npitch / 4; i += blockDim.x) {
+    uint4 v = __ldg(row + i);
+    c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+  }
+  typedef cub::BlockReduce<uint32_t, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  uint32_t tot = BR(tmp).Sum(c);
+  if (threadIdx.x == 0) ncount[s] = tot;
+}
+
+// site s is variable iff its column-AND nibble is 0
+__global__ void k_siteflags(const uint32_t *__restrict__ colmask, uint64_t L, uint8_t *__restrict__ flags) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 sites
+  if (g * 8 >= L) return;
+  uint32_t m = colmask[g];
+  uint64_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bool var = ((m >> (4 * i)) & 0xFu) == 0 && (g * 8 + i) < L;
+    out |= (uint64_t)(var ? 1 : 0) << (8 * i);
+  }
+  *reinterpret_cast<uint64_t *>(flags + g * 8) = out;
+}
+
+// K0b: bit-slice the variable sites. One warp per (word, sample-chunk); lane <-> site.
+__global__ void __launch_bounds__(256)
+k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uint32_t *__restrict__ site_idx, uint64_t V,
+         uint4 *__restrict__ planes, uint64_t Npad, uint32_t schunk) {
+  __shared__ uint8_t lut[256];
+  lut[threadIdx.x] = (uint8_t)base_mask(threadIdx.x);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t w = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w * 32 >= V) return;
+  const uint64_t v = w * 32 + lane;
+  const bool live = v < V;
+  const uint64_t site = live ? site_idx[v] : 0;
+  const uint64_t s0 = (uint64_t)blockIdx.y * schunk, s1 = min(n, s0 + schunk);
+#pragma unroll 4
+  for (uint64_t s = s0; s < s1; ++s) {
+    uint32_t m = live ? lut[seqs[s * pitch + site]] : 15u;
+    uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
+    uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
+    uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
+    uint32_t T = __ballot_sync(0xFFFFFFFFu, m & 8);
+    if (lane == 0) planes[w * Npad + s] = make_uint4(A, C, G, T);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: the pair sweep
+// ------------------------------------------------------------------------------------------
+struct SweepArgs {
+  const uint4 *planes;  // [Wp][Npad]
+  uint32_t Wp;          // padded word count (multiple of KC)
+  uint32_t Npad;
+  uint32_t n, i_end, j_start;
+  int32_t dist;
+  // tile list: row-blocks of this launch and the prefix of their tile counts
+  const uint32_t *rb_list;     // [n_rb]
+  const uint32_t *tile_prefix; // [n_rb + 1]
+  uint32_t n_rb;
+  uint32_t n_tiles;
+  uint32_t cb_min;  // first col-block allowed by j_start
+  unsigned long long *counter;
+  uint64_t *keys;
+  uint32_t *dvals;
+  unsigned long long cap;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int SWEEP_THREADS = 256;
+constexpr int STAGE_U4 = KC * TILE;  // uint4 per stage per side
+constexpr size_t SWEEP_SMEM = (size_t)STAGES * 2 * STAGE_U4 * sizeof(uint4);
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint4 *srow = reinterpret_cast<uint4 *>(smem_raw);       // [STAGES][KC][TILE]
+  uint4 *scol = srow + (size_t)STAGES * STAGE_U4;          // [STAGES][KC][TILE]
+  __shared__ __align__(8) uint64_t full[STAGES];
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t tx = tid & 15, ty = tid >> 4;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint32_t nk = a.Wp / KC;
+  uint32_t it = 0;  // running chunk counter (stage = it % STAGES, parity = (it / STAGES) & 1)
+
+  for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    // tile -> (row-block, col-block)
+    uint32_t lo = 0, hi = a.n_rb;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (a.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const uint32_t rb = a.rb_list[lo];
+    const uint32_t cb = max(rb, a.cb_min) + (tile - a.tile_prefix[lo]);
+    const uint4 *grow = a.planes + (size_t)rb * TILE;
+    const uint4 *gcol = a.planes + (size_t)cb * TILE;
+
+    auto issue = [&](uint32_t chunk, uint32_t slot) {
+      uint64_t *bar = &full[slot];
+      mbar_expect_tx(bar, 2u * STAGE_U4 * (uint32_t)sizeof(uint4));
+      uint4 *dr = srow + (size_t)slot * STAGE_U4;
+      uint4 *dc = scol + (size_t)slot * STAGE_U4;
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk) {
+        size_t goff = (size_t)(chunk * KC + kk) * a.Npad;
+        bulk_g2s(dr + kk * TILE, grow + goff, TILE * sizeof(uint4), bar);
+        bulk_g2s(dc + kk * TILE, gcol + goff, TILE * sizeof(uint4), bar);
+      }
+    };
+    if (tid == 0) {
+      for (uint32_t c = 0; c < (uint32_t)STAGES && c < nk; ++c) issue(c, (it + c) % STAGES);
+    }
+
+    uint32_t acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0;
+
+    for (uint32_t c = 0; c < nk; ++c, ++it) {
+      const uint32_t slot = it % STAGES;
+      mbar_wait(&full[slot], (it / STAGES) & 1u);
+      const uint4 *pr = srow + (size_t)slot * STAGE_U4 + ty;
+      const uint4 *pc = scol + (size_t)slot * STAGE_U4 + tx;
+#pragma unroll 2
+      for (int kk = 0; kk < KC; ++kk) {
+        uint4 r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = pr[kk * TILE + i * 16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 cv = pc[kk * TILE + j * 16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t m = (r[i].x & cv.x) | (r[i].y & cv.y) | (r[i].z & cv.z) | (r[i].w & cv.w);
+            acc[i][j] += __popc(m);
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && c + STAGES < nk) issue(c + STAGES, slot);
+    }
+
+    // ---- epilogue: threshold + append -------------------------------------------------
+    const uint32_t total_bits = a.Wp * 32u;
+    const uint32_t lane = tid & 31;
+    uint32_t cnt = 0;
+    uint64_t keep = 0;  // bit (i*8+j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t gi = rb * TILE + i * 16 + ty;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t gj = cb * TILE + j * 16 + tx;
+        const int32_t d = (int32_t)(total_bits - acc[i][j]);
+        const bool ok = gi < a.i_end && gj < a.n && gj > gi && gj >= a.j_start && d <= a.dist;
+        if (ok) {
+          keep |= 1ull << (i * 8 + j);
+          cnt++;
+        }
+      }
+    }
+    // warp-aggregated reservation
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (wtot) {
+      unsigned long long base = 0;
+      if (lane == 31) base = atomicAdd(a.counter, (unsigned long long)wtot);
+      base = __shfl_sync(0xFFFFFFFFu, base, 31);
+      unsigned long long pos = base + (incl - cnt);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((keep >> (i * 8 + j)) & 1ull) {
+            if (pos < a.cap) {
+              const uint32_t gi = rb * TILE + i * 16 + ty;
+              const uint32_t gj = cb * TILE + j * 16 + tx;
+              a.keys[pos] = ((uint64_t)gi << 32) | gj;
+              a.dvals[pos] = total_bits - acc[i][j];
+            }
+            pos++;
+          }
+        }
+      }
+    }
+  }
+}
+
+// expand sorted keys into the output columns
+__global__ void k_expand(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ dvals, uint64_t E,
+                         uint64_t *__restrict__ rows, uint64_t *__restrict__ cols, uint64_t *__restrict__ dist) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  uint64_t k = keys[e];
+  rows[e] = k >> 32;
+  cols[e] = k & 0xFFFFFFFFull;
+  dist[e] = dvals[e];
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: compared sites. nn = L - |N_i u N_j| = L - (|N_i| + |N_j| - |N_i n N_j|).
+// The intersection walks the block summaries (1 bit / 128 sites) and touches the N-plane only
+// where BOTH samples have an N in the block. One warp per edge.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ncomp(const uint64_t *__restrict__ keys, uint64_t E, const uint32_t *__restrict__ nplane, uint64_t npitch,
+        const uint8_t *__restrict__ nsum, uint64_t spitch, const uint32_t *__restrict__ ncount, uint64_t L,
+        uint64_t *__restrict__ ncomp) {
+  const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (e >= E) return;
+  const uint64_t k = keys[e];
+  const uint64_t i = k >> 32, j = k & 0xFFFFFFFFull;
+  const uint32_t *si = reinterpret_cast<const uint32_t *>(nsum + i * spitch);
+  const uint32_t *sj = reinterpret_cast<const uint32_t *>(nsum + j * spitch);
+  const uint4 *ni = reinterpret_cast<const uint4 *>(nplane + i * npitch);
+  const uint4 *nj = reinterpret_cast<const uint4 *>(nplane + j * npitch);
+  uint32_t inter = 0;
+  const uint64_t nq = spitch / 4;
+  for (uint64_t q = lane; q < nq; q += 32) {
+    uint32_t m = __ldg(si + q) & __ldg(sj + q);
+    while (m) {
+      uint32_t b = __ffs(m) - 1;
+      m &= m - 1;
+      uint64_t blk = q * 32 + b;
+      uint4 x = __ldg(ni + blk), y = __ldg(nj + blk);
+      inter += __popc(x.x & y.x) + __popc(x.y & y.y) + __popc(x.z & y.z) + __popc(x.w & y.w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) inter += __shfl_xor_sync(0xFFFFFFFFu, inter, o);
+  if (lane == 0) ncomp[e] = L - ((uint64_t)ncount[i] + ncount[j] - inter);
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+
+// Sweeps the device-resident ASCII matrix and appends edges (sorted) to `out`.
+void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,
+                  HostEdges &out, cudaStream_t st) {
+  tracs_stats_t &S = g_stats;
+  S.n_samples = n;
+  S.seq_length = L;
+  const uint64_t i_end = std::min<uint64_t>(o.i_end, n);
+  const uint64_t j_start = o.j_start;
+  if (n == 0 || i_end == 0 || j_start >= n) return;
+  if (n >= (1ull << 31)) throw std::runtime_error("too many samples");
+  if (pitch % 32 != 0 || pitch < round_up(L, 32)) throw std::runtime_error("device alignment pitch must be a multiple of 32 and >= L rounded up to 32");
+
+  Timer T(st), Ttot(st);
+  Ttot.start();
+
+  // ---- K0a ---------------------------------------------------------------------------
+  const uint64_t Lw = (L + 31) / 32;                       // words with sites
+  const uint64_t npitch = std::max<uint64_t>(32, round_up(Lw, 32));  // N-plane row pitch in words (whole warps)
+  const uint64_t spitch = round_up(npitch / 32, 4);        // summary bytes per row (uint32 granules)
+  DevBuf<uint32_t> colmask(std::max<uint64_t>(1, Lw * 4));
+  DevBuf<uint32_t> nplane, ncount;
+  DevBuf<uint8_t> nsum;
+  const bool want_n = o.want_ncomp != 0;
+  // N-plane is always produced by k_pack (same pass over the ASCII bytes)
+  nplane.alloc(n * npitch);
+  nsum.alloc(n * spitch);
+  ncount.alloc(n);
+  T.start();
+  TRACS_CK(cudaMemsetAsync(colmask.p, 0xFF, colmask.n * sizeof(uint32_t), st));
+  TRACS_CK(cudaMemsetAsync(nsum.p, 0, nsum.n, st));
+  if (L > 0) {
+    dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((n + PACK_SCHUNK - 1) / PACK_SCHUNK));
+    k_pack<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch);
+    S.kernel_launches++;
+    TRACS_CK(cudaGetLastError());
+    if (want_n) {
+      k_ncount<<<(unsigned)n, 256, 0, st>>>(nplane.p, npitch, ncount.p);
+      S.kernel_launches++;
+    }
+  } else {
+    TRACS_CK(cudaMemsetAsync(nplane.p, 0, nplane.n * sizeof(uint32_t), st));
+    TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
+  }
+  S.ms_pack = T.stop();
+
+  // ---- K0b: variable sites -> planes -----------------------------------------------------
+  T.start();
+  uint64_t V = 0;
+  DevBuf<uint32_t> site_idx;
+  if (L > 0) {
+    DevBuf<uint8_t> flags(round_up(L, 8));
+    k_siteflags<<<(unsigned)((Lw * 4 + 255) / 256), 256, 0, st>>>(colmask.p, L, flags.p);
+    S.kernel_launches++;
+    site_idx.alloc(L);
+    DevBuf<uint64_t> nsel(1);
+    size_t tmp_bytes = 0;
+    cub::CountingInputIterator<uint32_t> cnt_it(0);
+    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, cnt_it, flags.p, site_idx.p, nsel.p, (int64_t)L, st);
+    DevBuf<uint8_t> tmp(tmp_bytes);
+    cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, cnt_it, flags.p, site_idx.p, nsel.p, (int64_t)L, st);
+    S.kernel_launches += 2;
+    TRACS_CK(cudaMemcpyAsync(&V, nsel.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaStreamSynchronize(st));
+  }
+  const uint64_t W = (V + 31) / 32;
+  const uint32_t Wp = (uint32_t)std::max<uint64_t>(KC, round_up(W, KC));
+  const uint32_t Npad = (uint32_t)round_up(n, TILE);
+  S.n_variable_sites = V;
+  S.n_words = Wp;
+  DevBuf<uint4> planes((size_t)Wp * Npad);
+  TRACS_CK(cudaMemsetAsync(planes.p, 0xFF, planes.n * sizeof(uint4), st));
+  if (W > 0) {
+    const uint32_t schunk = 512;
+    dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
+    k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, planes.p, Npad, schunk);
+    S.kernel_launches++;
+    TRACS_CK(cudaGetLastError());
+  }
+  S.ms_compact = T.stop();
+  site_idx.release();
+
+  // ---- tile lists ------------------------------------------------------------------------
+  const uint32_t n_rb_all = (uint32_t)((i_end + TILE - 1) / TILE);
+  const uint32_t n_cb = Npad / TILE;
+  const uint32_t cb_min = (uint32_t)(j_start / TILE);
+  const int world = std::max(1, (int)o.shard_world), rank = std::max(0, (int)o.shard_rank);
+  if (rank >= world) throw std::runtime_error("shard_rank >= shard_world");
+  // row-blocks dealt boustrophedon (0..w-1, w-1..0, ...) so every shard gets equal triangle area
+  std::vector<uint32_t> my_rb;
+  for (uint32_t rb = 0; rb < n_rb_all; ++rb) {
+    uint32_t round = rb / world, pos = rb % world;
+    uint32_t owner = (round & 1) ? (world - 1 - pos) : pos;
+    if ((int)owner == rank && std::max(rb, cb_min) < n_cb) my_rb.push_back(rb);
+  }
+  auto pairs_of_rb = [&](uint32_t rb) -> uint64_t {
+    uint64_t tot = 0;
+    uint64_t r0 = (uint64_t)rb * TILE, r1 = std::min<uint64_t>(i_end, r0 + TILE);
+    for (uint64_t i = r0; i < r1; ++i) {
+      uint64_t j0 = std::max<uint64_t>(j_start, i + 1);
+      if (j0 < n) tot += n - j0;
+    }
+    return tot;
+  };
+  // bands: consecutive owned row-blocks whose pair count fits the edge buffer
+  const uint64_t CAP_MAX = 1ull << 28;
+  std::vector<std::pair<size_t, size_t>> bands;
+  std::vector<uint64_t> band_pairs;
+  {
+    size_t b0 = 0;
+    uint64_t acc = 0;
+    for (size_t k = 0; k < my_rb.size(); ++k) {
+      uint64_t p = pairs_of_rb(my_rb[k]);
+      S.n_pairs += p;
+      if (k > b0 && acc + p > CAP_MAX) {
+        bands.push_back({b0, k});
+        band_pairs.push_back(acc);
+        b0 = k;
+        acc = 0;
+      }
+      acc += p;
+    }
+    if (b0 < my_rb.size()) {
+      bands.push_back({b0, my_rb.size()});
+      band_pairs.push_back(acc);
+    }
+  }
+  if (bands.empty()) {
+    S.ms_total = Ttot.stop();
+    return;
+  }
+  uint64_t cap = 0;
+  for (uint64_t p : band_pairs) cap = std::max(cap, p);
+  cap = std::max<uint64_t>(cap, 1);
+
+  DevBuf<uint64_t> keys(cap), keys2(cap);
+  DevBuf<uint32_t> dv(cap), dv2(cap);
+  DevBuf<unsigned long long> counter(1);
+  DevBuf<uint32_t> d_rb(my_rb.size()), d_prefix(my_rb.size() + 1);
+  size_t sort_tmp_bytes = 0;
+  int end_bit = 32;
+  while ((1ull << (end_bit - 32)) < n) end_bit++;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, keys.p, keys2.p, dv.p, dv2.p, (int64_t)cap, 0, end_bit, st);
+  DevBuf<uint8_t> sort_tmp(sort_tmp_bytes);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    TRACS_CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+    attr_set = true;
+  }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, SWEEP_THREADS, SWEEP_SMEM);
+  occ = std::max(1, occ);
+
+  for (size_t b = 0; b < bands.size(); ++b) {
+    std::vector<uint32_t> rbs(my_rb.begin() + bands[b].first, my_rb.begin() + bands[b].second);
+    std::vector<uint32_t> prefix(rbs.size() + 1, 0);
+    for (size_t k = 0; k < rbs.size(); ++k) prefix[k + 1] = prefix[k] + (n_cb - std::max(rbs[k], cb_min));
+    const uint32_t n_tiles = prefix.back();
+    S.n_tiles += n_tiles;
+    TRACS_CK(cudaMemcpyAsync(d_rb.p, rbs.data(), rbs.size() * 4, cudaMemcpyHostToDevice, st));
+    TRACS_CK(cudaMemcpyAsync(d_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, st));
+    TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+    SweepArgs a;
+    a.planes = planes.p; a.Wp = Wp; a.Npad = Npad; a.n = (uint32_t)n; a.i_end = (uint32_t)i_end;
+    a.j_start = (uint32_t)j_start; a.dist = o.dist; a.rb_list = d_rb.p; a.tile_prefix = d_prefix.p;
+    a.n_rb = (uint32_t)rbs.size(); a.n_tiles = n_tiles; a.cb_min = cb_min; a.counter = counter.p;
+    a.keys = keys.p; a.dvals = dv.p; a.cap = cap;
+    T.start();
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)n_sm * occ);
+    k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
+    S.kernel_launches++;
+    TRACS_CK(cudaGetLastError());
+    S.ms_sweep += T.stop();
+
+    unsigned long long E = 0;
+    TRACS_CK(cudaMemcpyAsync(&E, counter.p, sizeof E, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaStreamSynchronize(st));
+    if (E > cap) throw std::runtime_error("internal error: edge buffer overflow");
+    if (E == 0) continue;
+
+    T.start();
+    cub::DeviceRadixSort::SortPairs(sort_tmp.p, sort_tmp_bytes, keys.p, keys2.p, dv.p, dv2.p, (int64_t)E, 0, end_bit, st);
+    S.kernel_launches += 4;
+    DevBuf<uint64_t> d_rows(E), d_cols(E), d_dist(E), d_nc;
+    k_expand<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dv2.p, E, d_rows.p, d_cols.p, d_dist.p);
+    S.kernel_launches++;
+    S.ms_sort += T.stop();
+
+    if (want_n) {
+      T.start();
+      d_nc.alloc(E);
+      k_ncomp<<<(unsigned)((E * 32 + 255) / 256), 256, 0, st>>>(keys2.p, E, nplane.p, npitch, nsum.p, spitch, ncount.p, L, d_nc.p);
+      S.kernel_launches++;
+      TRACS_CK(cudaGetLastError());
+      S.ms_ncomp += T.stop();
+    }
+    const size_t old = out.rows.size();
+    out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E); out.ncomp.resize(old + E, 0);
+    TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(out.dist.data() + old, d_dist.p, E * 8, cudaMemcpyDeviceToHost, st));
+    if (want_n) TRACS_CK(cudaMemcpyAsync(out.ncomp.data() + old, d_nc.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaStreamSynchronize(st));
+    S.d2h_bytes += E * 8 * (want_n ? 4 : 3);
+    S.n_edges += E;
+  }
+  S.ms_total = Ttot.stop();
+}
+
+}  // namespace tracs
