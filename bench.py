@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- pairwise SNP distance + transmission likelihood sweep on B200 (driver contract).
+
+Metric: site-pair comparisons/s = P*L / t  (P = N(N-1)/2 pairs, L = nominal alignment length), the
+metric BASELINE.json names. Workload at every GPU count: BASELINE.json configs[1] -- 10,000
+synthetic E. coli-like sequences x 5 Mb, ~1% variable sites, SNP threshold 20, TransCluster
+likelihood with sampling dates (SURVEY 8d "C2").
+
+  step          one whole pass of the hot path: ASCII alignment (resident in HBM) -> column masks +
+                N planes -> variable-site bit-planes -> all-pairs tile sweep with fused threshold ->
+                ordered edge list -> compared-site counts -> transmission likelihood -> edges on host.
+  value         P*L / step time, inputs resident in HBM (device-generated synthetic ASCII).
+  e2e           same metric through the C-ABI call that takes a HOST buffer (tracs_pairsnp_host):
+                H2D copy of the 50 GB ASCII matrix and D2H of the edge list inside the timed region.
+  --gpus N      strong scaling: the same alignment on every rank, triangle row-blocks dealt
+                boustrophedon across ranks, edge lists gathered to rank 0 over NCCL.
+  --impl reference   the unmodified reference (oracle/_ref, built from /root/reference/src) timed on
+                the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOAD = dict(name="C2: 10000 seqs x 5 Mb E. coli-like, 1% variable sites, dist<=20, transcluster with dates",
+                n=10000, L=5_000_000, p_var=0.01, n_clusters=100, mu=5.0, p_N=1e-3, p_amb=0.0, gc=0.508, seed=2,
+                n_days=180, gaps=2, dist=20, lamb=29.903, beta=73.0, threshold_Ek=0.01)
+SECONDS_IN_YEAR = 31556952.0
+
+
+def n_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU implementation on a bounded sample
+# ------------------------------------------------------------------------------------------------
+class RefSample:
+    """Bounded sample of the workload for the CPU reference: same generator, fewer/shorter sequences.
+    pair stage: n_p x L_p FASTA; the reference's serial loader is timed on the same file through the
+    empty-second-FASTA trick (pair loop empty: src/pairsnp.hpp:352-360,395)."""
+
+    def __init__(self, n_p=1024, L_p=100_000):
+        from tracs_b200 import synth
+        self.n_p, self.L_p = n_p, L_p
+        self.dir = tempfile.mkdtemp(prefix="tracs_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        w = WORKLOAD
+        seqs = synth.generate(n_p, L_p, p_var=w["p_var"], n_clusters=max(2, w["n_clusters"] * n_p // w["n"]), mu=w["mu"],
+                              p_N=w["p_N"], gc=w["gc"], seed=w["seed"], gaps=w["gaps"])
+        self.msa = os.path.join(self.dir, "sample.fasta")
+        synth.write_fasta(self.msa, seqs)
+        self.empty = os.path.join(self.dir, "empty.fasta")
+        open(self.empty, "w").close()
+        self.desc = ("reference pairsnp (oracle/_ref, unmodified src/pairsnp.hpp, -O3 -ffast-math) on %d seqs x %d bp of the "
+                     "same generator; pair stage = full call minus load-only call; value = projected whole-job rate at "
+                     "%d x %d: P*L / (N*L/load_rate + P*L/pair_rate)" % (n_p, L_p, w["n"], w["L"]))
+
+    def cleanup(self):
+        import shutil
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+    def step(self, mod, threads):
+        w = WORKLOAD
+        t0 = time.perf_counter()
+        mod.pairsnp(fasta=[self.msa, self.empty], n_threads=threads, dist=w["dist"], filter=False)
+        t_load = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r = mod.pairsnp(fasta=[self.msa], n_threads=threads, dist=w["dist"], filter=False)
+        t_full = time.perf_counter() - t0
+        t_pairs = max(t_full - t_load, 1e-6)
+        P_s = self.n_p * (self.n_p - 1) // 2
+        pair_rate = P_s * self.L_p / t_pairs
+        load_rate = self.n_p * self.L_p / t_load
+        P = w["n"] * (w["n"] - 1) // 2
+        t_proj = w["n"] * w["L"] / load_rate + P * w["L"] / pair_rate
+        return dict(t_step=t_load + t_full, pair_rate=pair_rate, load_rate=load_rate, projected=P * w["L"] / t_proj,
+                    edges=len(r[0]))
+
+
+def load_reference():
+    from oracle import refmod
+    if refmod.available():
+        mod, variant = refmod.load()
+        return mod, "reference", "oracle/_ref/%s" % variant
+    # the oracle port (plain C restatement) when the reference could not be compiled
+    from oracle import oracle
+
+    class _Port:
+        @staticmethod
+        def pairsnp(fasta, n_threads, dist, filter):
+            return oracle.pairsnp(fasta, n_threads=n_threads, dist=dist, filter=filter, as_lists=False)
+    return _Port, "port", "oracle/liboracle.so"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    mod, kind, what = load_reference()
+    cores = n_cores()
+    smp = RefSample()
+    try:
+        for _ in range(args.warmup):
+            smp.step(mod, cores)
+        t0 = time.perf_counter()
+        rs = [smp.step(mod, cores) for _ in range(args.steps)]
+        t = time.perf_counter() - t0
+    finally:
+        smp.cleanup()
+    val = float(np.median([r["projected"] for r in rs]))
+    line = {
+        "impl": "reference", "metric": "site-pair comparisons/s (P*L/t)", "value": val, "unit": "site-pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitset words", "data": "synthetic",
+        "config": {"workload": WORKLOAD["name"], "sample": smp.desc},
+        "cpu_baseline": {"value": val, "unit": "site-pairs/s", "cores": cores, "kind": kind, "sample": smp.desc, "what": what,
+                         "pair_stage_site_pairs_per_s": float(np.median([r["pair_rate"] for r in rs])),
+                         "load_bases_per_s": float(np.median([r["load_rate"] for r in rs]))},
+        "e2e": {"value": val, "unit": "site-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=None, help="override sample count (debug only; invalidates the headline)")
+    ap.add_argument("--L", type=int, default=None, help="override alignment length (debug only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import tracs_b200
+    from tracs_b200 import _lib
+    from tracs_b200.multi import gather_edges
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path")
+    torch.cuda.set_device(local)
+    _lib.check(_lib.lib().tracs_set_device(local))
+    device = torch.device("cuda", local)
+    dist_mod = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=device)
+
+    w = dict(WORKLOAD)
+    if args.n:
+        w["n"] = args.n
+        w["n_clusters"] = max(2, args.n // 100)
+    if args.L:
+        w["L"] = args.L
+    n, L = w["n"], w["L"]
+    P = n * (n - 1) // 2
+    pitch = (L + 127) // 128 * 128
+
+    # ---- synthetic input, generated in device memory ------------------------------------------
+    seqs = torch.empty(n * pitch, dtype=torch.uint8, device=device)
+    d_days = torch.empty(n, dtype=torch.int32, device=device)
+    tracs_b200.synth_device(seqs.data_ptr(), n, L, pitch, seed=w["seed"], p_var=w["p_var"], n_clusters=w["n_clusters"], mu=w["mu"],
+                            p_N=w["p_N"], p_amb=w["p_amb"], gc=w["gc"], n_days=w["n_days"], gaps=w["gaps"], dev_days=d_days.data_ptr())
+    days = d_days.cpu().numpy()
+    kw = dict(dist=w["dist"], days=days, lamb=w["lamb"], beta=w["beta"], threshold_Ek=w["threshold_Ek"],
+              shard_rank=rank, shard_world=world)
+
+    peak = tracs_b200.int_peak() if rank == 0 else None
+
+    def step():
+        res = tracs_b200.pairsnp_device(seqs.data_ptr(), n, L, pitch, **kw)
+        st = tracs_b200.last_stats()
+        merged = gather_edges(res, rank, world, dist_mod, torch, device) if world > 1 else res
+        return res, st, merged
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats = []
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        res, st, merged = step()
+        stats.append(st)
+    ev1.record()
+    sync()
+    t_wall = time.perf_counter() - t_wall0
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist_mod.all_reduce(t_ms, op=dist_mod.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    ms_per_step = ms / args.steps
+    value = P * L / (ms_per_step * 1e-3)
+
+    def avg(k):
+        return float(np.mean([s[k] for s in stats]))
+
+    line = None
+    if rank == 0:
+        st = stats[-1]
+        n_edges = len(merged["rows"]) if isinstance(merged, dict) else merged.shape[1]
+        launches = int(sum(s["kernel_launches"] for s in stats))
+        # ---- roofline of the dominant kernel (k_sweep), INT-pipe bound --------------------------
+        # algorithmic work: 6 INT instructions per 32-site word-pair (1 AND + 3 AND-OR LOP3 + POPC + ADD;
+        # SURVEY 8d) over the variable sites only: pairs_in_tiles * ceil(V_eff/32).
+        W_alg = (st["n_variable_sites"] + 31) // 32
+        shard_pairs = st["n_pairs"]
+        alg_instr = shard_pairs * W_alg * 6
+        t_sweep = avg("ms_sweep") * 1e-3
+        peak_wp = min(peak["lop3_per_s"] / 4.0, peak["popc_per_s"])
+        roof = {"bound": "int_pipe", "kernel": "k_sweep", "achieved": alg_instr / t_sweep / 1e9, "peak": peak_wp * 6 / 1e9,
+                "unit": "Ginstr/s", "frac": (alg_instr / t_sweep) / (peak_wp * 6), "traffic": None,
+                "peak_source": "measured in this run (tracs_int_peak: register-resident LOP3 and POPC loops; a word-pair needs "
+                               "4 LOP3 on the 64-lane ALU pipe and 1 POPC on the 16-lane pipe => min(lop3/4, popc) word-pairs/s)",
+                "achieved_wordpairs_per_s": shard_pairs * W_alg / t_sweep, "ms_per_launch": avg("ms_sweep"),
+                "lop3_per_s": peak["lop3_per_s"], "popc_per_s": peak["popc_per_s"],
+                "mix_wordpairs_per_s": peak["mix_wordpairs_per_s"], "mix_imad_wordpairs_per_s": peak["mix_imad_wordpairs_per_s"]}
+        prof = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+        if os.path.exists(prof):
+            try:
+                roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        hbm = None
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        stages = {k: avg(k) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_sort", "ms_ncomp", "ms_trans", "ms_total")}
+        if hbm:
+            stages["pack_hbm_frac_of_measured"] = (n * L / (avg("ms_pack") * 1e-3) / 1e9) / hbm
+        line = {
+            "metric": "site-pair comparisons/s (P*L/t)", "value": value, "unit": "site-pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 bit-planes (int32 counts), f64 likelihood", "data": "synthetic (device-generated ASCII alignment, seeded)",
+            "config": {"workload": w["name"], "n": n, "L": L, "pairs": P, "variable_sites": int(st["n_variable_sites"]),
+                       "words": int(st["n_words"]), "edges": int(n_edges), "dist": w["dist"],
+                       "parallelism": "triangle row-blocks dealt boustrophedon over %d GPU(s); ingest replicated" % world,
+                       "l2": "inputs (%.1f GB ASCII) larger than L2; no flush needed" % (n * pitch / 1e9)},
+            "clocks": clk, "gpu_launches": launches, "roofline": roof, "stages_ms": stages,
+            "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        }
+
+    # ---- e2e: host buffer through the C ABI (N=1 only: the path has one host) ----------------------
+    if rank == 0 and world == 1 and not args.no_e2e:
+        e2e = {"value": None, "unit": "site-pairs/s", "h2d_bytes_per_step": n * L, "d2h_bytes_per_step": None}
+        try:
+            host = None
+            try:
+                host = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
+                e2e["host_memory"] = "pinned"
+            except Exception:
+                host = torch.empty((n, L), dtype=torch.uint8)
+                e2e["host_memory"] = "pageable"
+            # fill the host buffer with the same alignment (setup, untimed)
+            rows = 500
+            for r0 in range(0, n, rows):
+                r1 = min(n, r0 + rows)
+                host[r0:r1].copy_(seqs[r0 * pitch:r1 * pitch].view(r1 - r0, pitch)[:, :L])
+            torch.cuda.synchronize()
+            del seqs
+            torch.cuda.empty_cache()
+            hp = host.numpy()
+            o, keep = tracs_b200.api.make_opts(**kw)
+
+            def e2e_step():
+                e = _lib.Edges()
+                _lib.check(_lib.lib().tracs_pairsnp_host(hp.ctypes.data, n, L, L, C.byref(o), C.byref(e)))
+                return _lib.take_edges(e, names=False)
+
+            e2e_step()
+            torch.cuda.synchronize()
+            ev0.record()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                r2 = e2e_step()
+            ev1.record()
+            torch.cuda.synchronize()
+            te = (time.perf_counter() - t0) / args.e2e_steps
+            st2 = tracs_b200.last_stats()
+            e2e["value"] = P * L / te
+            e2e["ms_per_step"] = te * 1e3
+            e2e["steps"] = args.e2e_steps
+            e2e["d2h_bytes_per_step"] = int(st2["d2h_bytes"])
+            e2e["edges_equal_device_path"] = bool(np.array_equal(r2["rows"], res["rows"]) and np.array_equal(r2["dist"], res["dist"])
+                                                  and np.array_equal(r2["ncomp"], res["ncomp"]))
+            e2e["api"] = "tracs_pairsnp_host (C ABI, host ASCII matrix) incl. fused transmission likelihood"
+            del host
+        except Exception as ex:  # report, never fake
+            e2e["error"] = repr(ex)
+        line["e2e"] = e2e
+    elif rank == 0:
+        line["e2e"] = {"value": None, "unit": "site-pairs/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                       "note": "measured at N=1 only (one host buffer)" if world > 1 else "skipped (--no-e2e)"}
+
+    # ---- cpu baseline beside it (rank 0, N=1) -----------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            mod, kind, what = load_reference()
+            smp = RefSample()
+            try:
+                r = smp.step(mod, n_cores())
+            finally:
+                smp.cleanup()
+            line["cpu_baseline"] = {"value": r["projected"], "unit": "site-pairs/s", "cores": n_cores(), "kind": kind, "sample": smp.desc,
+                                    "what": what, "pair_stage_site_pairs_per_s": r["pair_rate"], "load_bases_per_s": r["load_rate"]}
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "error": repr(ex)}
+    elif rank == 0:
+        line["cpu_baseline"] = {"value": None, "note": "timed at N=1 only"}
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist_mod.barrier()
+        dist_mod.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -98,6 +98,16 @@ int tracs_pairsnp_device(const uint8_t *dev_seqs, size_t n, size_t L, size_t pit
 
 void tracs_edges_free(tracs_edges_t *e);
 
+/* The loader half of pairsnp on its own (src/pairsnp.hpp:62-220 + src/kseq.h:170-208 record
+ * semantics): FASTA/FASTQ(.gz) -> ASCII matrix seqs[n][L] (malloc'ed, pitch == L) + names. Host only.
+ * Errors like the reference: "Error reading FASTA!", "... variable sequence lengths!". */
+int tracs_read_fasta(const char *path, int n_threads, uint8_t **seqs, size_t *n, size_t *L, char ***names);
+void tracs_free_fasta(uint8_t *seqs, char **names, size_t n);
+
+/* Row-blocks (128 samples each) that shard `rank` of `world` sweeps (boustrophedon deal).
+ * out: caller-allocated, n_rowblocks entries. Host only. */
+int tracs_shard_rowblocks(uint32_t n_rowblocks, int32_t world, int32_t rank, uint32_t *out, uint32_t *n_out);
+
 /* Replaces TRACS.trans_dist(snpdiff, datediff, lamb, beta, threshold_Ek) --
  * src/python_bindings.cpp:19-21, src/transcluster.hpp:240-287. p0_log and eK: caller-allocated,
  * n doubles each. */
@@ -126,6 +136,9 @@ int tracs_min_over_refs(const uint64_t *a, const uint64_t *b, const double *val,
 const char *tracs_last_error(void);
 int tracs_last_stats(tracs_stats_t *out);
 int tracs_device_count(void);
+/* Scratch buffers are cached in the device's default memory pool between calls; this returns them
+ * to the driver. */
+int tracs_trim(void);
 int tracs_set_device(int device);
 
 /* ---- bench / test utilities (not in the reference) ------------------------------------------ */
@@ -154,8 +167,9 @@ int tracs_memcpy_d2h(void *dst, const void *src, size_t bytes);
 int tracs_memcpy_h2d(void *dst, const void *src, size_t bytes);
 
 /* Measures the INT-pipe peak on the current device with register-resident loops.
- * out[0] = LOP3 warp-lane ops/s, out[1] = POPC ops/s, out[2] = IADD ops/s,
- * out[3] = word-pairs/s of the (4 LOP3 + POPC + ADD) mix, out[4] = SM clock MHz seen (cycles/time). */
+ * out[0] = LOP3 lane-ops/s, out[1] = POPC lane-ops/s, out[2] = IADD lane-ops/s,
+ * out[3] = word-pairs/s of the sweep's (4 LOP3 + POPC + ADD) mix, out[4] = same with the add
+ * issued as IMAD (FMA pipe), out[5] = SM count. */
 int tracs_int_peak(double out[8]);
 
 #ifdef __cplusplus

@@ -1,0 +1,160 @@
+"""CPU: the C-ABI library loads, exports every symbol include/tracs_b200.h declares, fails loudly
+without a GPU, and its host-only entry points (FASTA loader, lprob_k_given_N, calculate_posteriors,
+shard dealing) match the oracle / golden fixtures."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy.special import gammaln
+
+import tracs_b200
+from tracs_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+G = json.load(open(os.path.join(GOLD, "golden.json")))
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "tracs_b200.h")).read()
+    declared = set(re.findall(r"\b(tracs_[a-z0-9_]+)\s*\(", hdr, flags=re.I))
+    declared = {d for d in declared if not d.endswith("_t")}
+    assert len(declared) >= 20
+    lib = C.CDLL(_lib.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), "missing export: " + sym
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+def test_struct_layouts_match_c():
+    # sizes the C compiler gives for the structs in include/tracs_b200.h (x86-64 SysV)
+    assert C.sizeof(_lib.Edges) == 12 * 8
+    assert C.sizeof(_lib.Stats) == 10 * 8 + 7 * 4 + 4
+    assert C.sizeof(_lib.Opts) == 8 + 16 + 16 + 8 + 24 + 8
+    assert C.sizeof(_lib.Synth) == 32 + 8 + 8 + 32 + 8
+
+
+def test_no_gpu_fails_loudly():
+    if _lib.lib().tracs_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tracs_b200.trans_dist([1], [0.1], 29.9, 73.0, 0.01)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tracs_b200.pairsnp_matrix(np.full((2, 4), 65, np.uint8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tracs_b200.pairsnp(fasta=[os.path.join(GOLD, "kat.fasta")], n_threads=1, dist=5, filter=False)
+
+
+def test_product_does_not_import_oracle():
+    import subprocess, sys
+    code = "import sys; import tracs_b200, tracs_b200.distance, tracs_b200.multi; tracs_b200.install_dropin(); " \
+           "assert not [m for m in sys.modules if m.startswith('oracle')], 'oracle imported by product'"
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tracs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_dropin_module_surface():
+    T = tracs_b200.install_dropin()
+    for name in ("pairsnp", "trans_dist", "lprob_k_given_N", "calculate_posteriors"):
+        assert callable(getattr(T, name))
+    # keyword names of src/python_bindings.cpp:12-25
+    import inspect
+    assert list(inspect.signature(T.pairsnp).parameters) == ["fasta", "n_threads", "dist", "filter"]
+    assert list(inspect.signature(T.trans_dist).parameters) == ["snpdiff", "datediff", "lamb", "beta", "threshold_Ek"]
+    assert list(inspect.signature(T.lprob_k_given_N).parameters) == ["N", "k", "delta", "lamb", "beta", "lgamma"]
+    assert list(inspect.signature(T.calculate_posteriors).parameters) == ["counts", "alphas", "keep", "threshold"]
+
+
+def test_lprob_k_given_N_kat_and_golden():
+    lp, lhs = tracs_b200.lprob_k_given_N(7, 4, 0.16963, 3, 52, gammaln(range(20)))  # reference tests/test_llk.py:21-29
+    assert abs(lp + 17.9565184209608) < 1e-6 and abs(lhs - 12.0861694243766) < 1e-6
+    for c in G["lprob_k_given_N"]:
+        N, k, delta, lamb, beta = c["args"]
+        assert np.allclose(tracs_b200.lprob_k_given_N(int(N), int(k), delta, lamb, beta, gammaln(range(40))), c["out"], rtol=1e-12)
+    with pytest.raises(IndexError):
+        tracs_b200.lprob_k_given_N(7, 4, 0.1, 3, 52, gammaln(range(5)))
+
+
+def test_calculate_posteriors_golden():
+    for c in G["calculate_posteriors"]:
+        out = tracs_b200.calculate_posteriors(np.array(c["counts"]), c["alphas"], c["keep"], c["threshold"])
+        assert out.shape == np.array(c["counts"]).shape
+        assert np.allclose(out, c["out"], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("name", ["aln0.fasta", "aln1.fasta.gz", "aln2.fasta", "aln3.fasta.gz", "aln4.fasta", "query.fasta", "db.fasta.gz"])
+def test_fasta_loader_golden(oracle_mod, name):
+    a, names = tracs_b200.read_fasta(os.path.join(GOLD, name))
+    exp = oracle_mod.pairsnp([os.path.join(GOLD, name)], dist=-1)
+    assert names == exp[3]
+    m = oracle_mod.masks_of(a)
+    assert m.shape[0] == len(names)
+
+
+def test_fasta_loader_record_semantics(oracle_mod, tmp_path):
+    # kseq semantics (reference src/kseq.h:170-208): junk before the first header, names end at
+    # whitespace, '>'/'@'/'+' end a sequence anywhere, blank lines / CRLF / spaces dropped, FASTQ blocks.
+    cases = {
+        "plain": b">a desc here\nACGT\nAC\n>b\nAC-NNT\n",
+        "junk_crlf": b"junk line\r\n>a\tx\r\nAC GT\r\n\r\nAC\r\n>b\r\nACGTAC\r\n",
+        "no_trailing_newline": b">a\nACGT\n>b\nACGA",
+        "fastq": b"@r1 d\nACGT\n+\nIIII\n@r2\nACGA\n+r2\nII!I\n",
+        "fastq_multi": b"@r1\nAC\nGT\n+\nII\nII\n@r2\nACGA\n+\nIIII\n",
+        "gt_inside": b">a\nAC>b\nGT\n",
+        "empty_seq": b">a\n>b\n",
+        "single": b">only\nACGTNNNN",
+        "lower_iupac": b">a\nacgtmrwsykvhdbn-x?.\n>b\nACGTMRWSYKVHDBN-X?.\n",
+    }
+    for tag, data in cases.items():
+        p = str(tmp_path / (tag + ".fa"))
+        open(p, "wb").write(data)
+        a, names = tracs_b200.read_fasta(p)
+        exp = oracle_mod.pairsnp([p], dist=2147483647)
+        assert names == exp[3], tag
+        if len(names) >= 2 and a.shape[1] > 0:
+            got = oracle_mod.pairsnp_ascii(a, dist=2147483647)
+            assert got[2].tolist() == exp[2] and got[4].tolist() == exp[5], tag
+    p = str(tmp_path / "ragged.fa")
+    open(p, "wb").write(b">a\nACGT\n>b\nACG\n")
+    with pytest.raises(RuntimeError, match="variable sequence lengths"):
+        tracs_b200.read_fasta(p)
+    p = str(tmp_path / "trunc.fq")
+    open(p, "wb").write(b"@r1\nACGT\n+\nII")
+    with pytest.raises(RuntimeError, match="Error reading FASTA"):
+        tracs_b200.read_fasta(p)
+    with pytest.raises(RuntimeError, match="Error reading FASTA"):
+        tracs_b200.read_fasta(str(tmp_path / "does_not_exist.fa"))
+
+
+def test_fasta_loader_live_reference_errors(ref_mod, tmp_path):
+    p = str(tmp_path / "ragged.fa")
+    open(p, "wb").write(b">a\nACGT\n>b\nACG\n")
+    with pytest.raises(RuntimeError, match="variable sequence lengths"):
+        ref_mod.pairsnp(fasta=[p], n_threads=1, dist=1, filter=False)
+
+
+def test_fasta_loader_large_roundtrip(tmp_path):
+    s = synth.generate(50, 30011, p_var=0.02, seed=8, lowercase=0.05)
+    for gz, width in ((False, 0), (True, 61)):
+        p = str(tmp_path / ("big.fa" + (".gz" if gz else "")))
+        synth.write_fasta(p, s, width=width, descriptions=True)
+        a, names = tracs_b200.read_fasta(p)
+        assert names == ["s%d" % i for i in range(50)] and np.array_equal(a, s)
+
+
+def test_shard_dealing_covers_and_balances():
+    for n_rb, world in ((1, 1), (7, 2), (79, 8), (782, 8), (5, 8), (16, 4)):
+        parts = [tracs_b200.shard_rowblocks(n_rb, world, r) for r in range(world)]
+        allrb = np.sort(np.concatenate(parts))
+        assert allrb.tolist() == list(range(n_rb))
+        # triangle work of row-block rb ~ (n_rb - rb) tiles; boustrophedon keeps shards within one round of each other
+        work = [sum(n_rb - int(rb) for rb in p) for p in parts]
+        if n_rb >= 4 * world:
+            assert max(work) - min(work) <= 2 * world + n_rb % (2 * world) * world

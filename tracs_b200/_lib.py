@@ -45,9 +45,9 @@ class Synth(C.Structure):
 # every symbol include/tracs_b200.h declares
 SYMBOLS = ["tracs_pairsnp", "tracs_pairsnp_host", "tracs_pairsnp_device", "tracs_edges_free", "tracs_trans_dist",
            "tracs_lprob_k_given_N", "tracs_calculate_posteriors", "tracs_min_over_refs", "tracs_last_error",
-           "tracs_last_stats", "tracs_device_count", "tracs_set_device", "tracs_synth_device", "tracs_dev_alloc",
+           "tracs_last_stats", "tracs_device_count", "tracs_trim", "tracs_set_device", "tracs_synth_device", "tracs_dev_alloc",
            "tracs_dev_free", "tracs_host_alloc_pinned", "tracs_host_free_pinned", "tracs_memcpy_d2h",
-           "tracs_memcpy_h2d", "tracs_int_peak"]
+           "tracs_memcpy_h2d", "tracs_int_peak", "tracs_read_fasta", "tracs_free_fasta", "tracs_shard_rowblocks"]
 
 _lib = None
 
@@ -78,6 +78,11 @@ def lib():
         L.tracs_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.tracs_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.tracs_int_peak.argtypes = [C.c_void_p]
+        L.tracs_read_fasta.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                       C.POINTER(C.POINTER(C.c_char_p))]
+        L.tracs_free_fasta.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_char_p), C.c_size_t]
+        L.tracs_free_fasta.restype = None
+        L.tracs_shard_rowblocks.argtypes = [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 

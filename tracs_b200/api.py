@@ -122,11 +122,35 @@ def synth_device(dev_ptr, n, L, pitch, seed=1, p_var=0.01, n_clusters=20, mu=5.0
     _lib.check(_lib.lib().tracs_synth_device(C.byref(cfg), C.c_void_p(dev_ptr), C.c_void_p(dev_days) if dev_days else None))
 
 
+def read_fasta(path, n_threads=1):
+    """FASTA/FASTQ(.gz) -> (uint8[n][L] ASCII matrix, names). Host only (the loader half of pairsnp)."""
+    seqs = C.POINTER(C.c_uint8)()
+    names = C.POINTER(C.c_char_p)()
+    n, L = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(_lib.lib().tracs_read_fasta(os.fsencode(os.fspath(path)), int(n_threads), C.byref(seqs), C.byref(n), C.byref(L), C.byref(names)))
+    try:
+        if n.value and L.value:
+            a = np.ctypeslib.as_array(seqs, shape=(n.value * L.value,)).reshape(n.value, L.value).copy()
+        else:
+            a = np.zeros((n.value, L.value), np.uint8)
+        nm = [names[i].decode() for i in range(n.value)]
+    finally:
+        _lib.lib().tracs_free_fasta(seqs, names, n.value)
+    return a, nm
+
+
+def shard_rowblocks(n_rowblocks, world, rank):
+    out = np.zeros(max(1, n_rowblocks), np.uint32)
+    k = C.c_uint32(0)
+    _lib.check(_lib.lib().tracs_shard_rowblocks(n_rowblocks, world, rank, out.ctypes.data, C.byref(k)))
+    return out[:k.value].copy()
+
+
 def int_peak():
     out = np.zeros(8, np.float64)
     _lib.check(_lib.lib().tracs_int_peak(out.ctypes.data))
     return {"lop3_per_s": out[0], "popc_per_s": out[1], "iadd_per_s": out[2], "mix_wordpairs_per_s": out[3],
-            "sm_mhz_lop3": out[4], "n_sm": int(out[5]), "sm_mhz_mix": out[6]}
+            "mix_imad_wordpairs_per_s": out[4], "n_sm": int(out[5])}
 
 
 def last_stats():

@@ -16,6 +16,19 @@ thread_local std::string g_err;
 thread_local tracs_stats_t g_stats;
 void set_error(const std::string &msg) { g_err = msg; }
 
+void pool_init() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (done_for == dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_for = dev;
+}
+
 static void require_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -140,9 +153,9 @@ __global__ void k_synth_days(uint64_t n, uint64_t seed, uint32_t n_days, int32_t
 // ---- INT pipe peak micro-benchmarks -------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256) k_peak(uint32_t *out, int iters, long long *cycles) {
-  uint32_t x[16];
+  uint32_t x[48];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+  for (int i = 0; i < 48; ++i) x[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
   uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
@@ -162,30 +175,32 @@ __global__ void __launch_bounds__(256) k_peak(uint32_t *out, int iters, long lon
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int i = 0; i < 16; ++i) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(x[(i + 3) & 15]));
-    } else {  // sweep mix on register operands: 2 row x 2 col uint4, 4 word-pairs x 4 repeats
+    } else {
+      // the sweep's per-word-pair mix on register operands: 8 row quads x 4 col quads = 32
+      // distinct word-pairs per iteration (4 LOP3 + POPC + ADD each); every row quad changes each
+      // iteration so nothing is loop-invariant or common between pairs.
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 4; ++j) {
+          uint32_t m;
+          asm volatile("and.b32 %0, %1, %2;" : "=r"(m) : "r"(x[i * 4 + 0]), "r"(x[32 + j * 4 + 0]));
+          asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 1]), "r"(x[32 + j * 4 + 1]));
+          asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 2]), "r"(x[32 + j * 4 + 2]));
+          asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 3]), "r"(x[32 + j * 4 + 3]));
+          uint32_t p;
+          asm volatile("popc.b32 %0, %1;" : "=r"(p) : "r"(m));
+          if (MODE == 3) acc[(i + j) & 7] += p;
+          else asm volatile("mad.lo.u32 %0, %1, 1, %0;" : "+r"(acc[(i + j) & 7]) : "r"(p));
+        }
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint32_t m;
-            asm volatile("and.b32 %0, %1, %2;" : "=r"(m) : "r"(x[i * 4 + 0]), "r"(x[8 + j * 4 + 0]));
-            asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 1]), "r"(x[8 + j * 4 + 1]));
-            asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 2]), "r"(x[8 + j * 4 + 2]));
-            asm volatile("lop3.b32 %0, %1, %2, %0, 0xEA;" : "+r"(m) : "r"(x[i * 4 + 3]), "r"(x[8 + j * 4 + 3]));
-            uint32_t p;
-            asm volatile("popc.b32 %0, %1;" : "=r"(p) : "r"(m));
-            acc[(i * 2 + j) + 4 * (r & 1)] += p;
-          }
-        x[r] += acc[r];  // keep operands changing so nothing hoists
-      }
+      for (int i = 0; i < 8; ++i) x[i * 4] += acc[i] + it;
     }
   }
   const long long t1 = clock64();
   uint32_t s = 0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s ^= x[i];
+  for (int i = 0; i < 48; ++i) s ^= x[i];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += acc[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
@@ -310,6 +325,40 @@ int tracs_pairsnp(const char *const *paths, int n_paths, int n_threads, int32_t 
     out->n_names = names.size();
     out->names = (char **)malloc(std::max<size_t>(1, names.size()) * sizeof(char *));
     for (size_t i = 0; i < names.size(); ++i) out->names[i] = strdup(names[i].c_str());
+  });
+}
+
+int tracs_read_fasta(const char *path, int n_threads, uint8_t **seqs, size_t *n, size_t *L, char ***names) {
+  *seqs = nullptr; *names = nullptr; *n = 0; *L = 0;
+  return guarded([&] {
+    std::vector<uint8_t> ascii;
+    std::vector<std::string> nm;
+    uint64_t len = 0;
+    const uint64_t cnt = read_fasta(path, n_threads, ascii, nm, len);
+    *seqs = (uint8_t *)malloc(std::max<size_t>(1, ascii.size()));
+    if (!ascii.empty()) memcpy(*seqs, ascii.data(), ascii.size());
+    *names = (char **)malloc(std::max<size_t>(1, nm.size()) * sizeof(char *));
+    for (size_t i = 0; i < nm.size(); ++i) (*names)[i] = strdup(nm[i].c_str());
+    *n = cnt;
+    *L = len;
+  });
+}
+
+void tracs_free_fasta(uint8_t *seqs, char **names, size_t n) {
+  free(seqs);
+  if (names) {
+    for (size_t i = 0; i < n; ++i) free(names[i]);
+    free(names);
+  }
+}
+
+int tracs_shard_rowblocks(uint32_t n_rowblocks, int32_t world, int32_t rank, uint32_t *out, uint32_t *n_out) {
+  return guarded([&] {
+    if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("shard_rank >= shard_world");
+    uint32_t k = 0;
+    for (uint32_t rb = 0; rb < n_rowblocks; ++rb)
+      if (shard_owner(rb, world) == rank) out[k++] = rb;
+    *n_out = k;
   });
 }
 
@@ -460,6 +509,17 @@ int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev
   });
 }
 
+int tracs_trim(void) {
+  return guarded([&] {
+    int dev = 0;
+    TRACS_CK(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    TRACS_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    TRACS_CK(cudaDeviceSynchronize());
+    TRACS_CK(cudaMemPoolTrimTo(pool, 0));
+  });
+}
+
 int tracs_dev_alloc(void **p, size_t bytes) {
   return guarded([&] { require_device(); TRACS_CK(cudaMalloc(p, bytes)); });
 }
@@ -485,38 +545,35 @@ int tracs_int_peak(double out[8]) {
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    const int blocks = n_sm * 8, threads = 256, iters = 4096;
+    const int blocks = n_sm * 4, threads = 256, iters = 4096;
     DevBuf<uint32_t> sink((size_t)blocks * threads);
     DevBuf<long long> cyc(1);
     Timer T(0);
-    auto run = [&](int mode) -> std::pair<double, double> {
+    auto run = [&](int mode) -> double {
       float best = 1e30f;
-      long long cycles = 0;
       for (int rep = 0; rep < 4; ++rep) {
         T.start();
         switch (mode) {
           case 0: k_peak<0><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
           case 1: k_peak<1><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
           case 2: k_peak<2><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
-          default: k_peak<3><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
+          case 3: k_peak<3><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
+          default: k_peak<4><<<blocks, threads>>>(sink.p, iters, cyc.p); break;
         }
         float ms = T.stop();
         TRACS_CK(cudaGetLastError());
         if (rep > 0 && ms < best) best = ms;
       }
-      TRACS_CK(cudaMemcpy(&cycles, cyc.p, 8, cudaMemcpyDeviceToHost));
-      return {(double)best * 1e-3, (double)cycles};
+      return (double)best * 1e-3;
     };
     const double lanes = (double)blocks * threads * iters;
-    auto r0 = run(0), r1 = run(1), r2 = run(2), r3 = run(3);
-    out[0] = lanes * 64 / r0.first;
-    out[1] = lanes * 64 / r1.first;
-    out[2] = lanes * 64 / r2.first;
-    out[3] = lanes * 16 / r3.first;  // word-pairs / s
-    // one CTA's clock64 span over the kernel's wall time ~ SM clock (CTAs run in 1+ waves: 8/SM resident)
-    out[4] = r0.second / r0.first / 1e6;
+    out[0] = lanes * 64 / run(0);  // LOP3 lane-ops / s
+    out[1] = lanes * 64 / run(1);  // POPC
+    out[2] = lanes * 64 / run(2);  // IADD
+    out[3] = lanes * 32 / run(3);  // word-pairs / s, add on the ALU pipe
+    out[4] = lanes * 32 / run(4);  // word-pairs / s, add as IMAD (FMA pipe)
     out[5] = (double)n_sm;
-    out[6] = r3.second / r3.first / 1e6;
+    out[6] = 0;
     out[7] = 0;
   });
 }

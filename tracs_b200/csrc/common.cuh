@@ -28,6 +28,10 @@ struct CudaError {
     }                                                                                              \
   } while (0)
 
+// Keeps freed blocks in the default memory pool instead of returning them to the driver, so the
+// multi-GB scratch buffers of one call are reused by the next (tracs_trim() releases them).
+void pool_init();
+
 // RAII device buffer
 template <typename T>
 struct DevBuf {
@@ -37,13 +41,17 @@ struct DevBuf {
   explicit DevBuf(size_t count) { alloc(count); }
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
+  // stream-ordered allocation from the device's default pool (kept across calls: see pool_init)
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) TRACS_CK(cudaMalloc((void **)&p, count * sizeof(T)));
+    if (count) {
+      pool_init();
+      TRACS_CK(cudaMallocAsync((void **)&p, count * sizeof(T), (cudaStream_t)0));
+    }
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, (cudaStream_t)0);
     p = nullptr;
     n = 0;
   }
@@ -85,6 +93,13 @@ struct Alignment {
 // appends the records of `path`; returns number of records read; throws std::runtime_error
 uint64_t read_fasta(const char *path, int n_threads, std::vector<uint8_t> &ascii, std::vector<std::string> &names,
                     uint64_t &L);
+
+// Static multi-GPU partition: row-blocks of 128 samples are dealt boustrophedon
+// (0..w-1, w-1..0, ...) so every shard sweeps (nearly) the same triangle area.
+inline int shard_owner(uint32_t row_block, int world) {
+  const uint32_t round = row_block / (uint32_t)world, pos = row_block % (uint32_t)world;
+  return (round & 1u) ? (world - 1 - (int)pos) : (int)pos;
+}
 
 // host-side edge columns produced by the sweep (sorted by (row, col))
 struct HostEdges {

@@ -511,9 +511,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   // row-blocks dealt boustrophedon (0..w-1, w-1..0, ...) so every shard gets equal triangle area
   std::vector<uint32_t> my_rb;
   for (uint32_t rb = 0; rb < n_rb_all; ++rb) {
-    uint32_t round = rb / world, pos = rb % world;
-    uint32_t owner = (round & 1) ? (world - 1 - pos) : pos;
-    if ((int)owner == rank && std::max(rb, cb_min) < n_cb) my_rb.push_back(rb);
+    if (shard_owner(rb, world) == rank && std::max(rb, cb_min) < n_cb) my_rb.push_back(rb);
   }
   auto pairs_of_rb = [&](uint32_t rb) -> uint64_t {
     uint64_t tot = 0;
@@ -606,7 +604,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
 
     T.start();
     cub::DeviceRadixSort::SortPairs(sort_tmp.p, sort_tmp_bytes, keys.p, keys2.p, dv.p, dv2.p, (int64_t)E, 0, end_bit, st);
-    S.kernel_launches += 4;
+    S.kernel_launches += 2 + (end_bit + 7) / 8;  // histogram + scan + one onesweep pass per 8 key bits
     DevBuf<uint64_t> d_rows(E), d_cols(E), d_dist(E), d_nc;
     k_expand<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dv2.p, E, d_rows.p, d_cols.p, d_dist.p);
     S.kernel_launches++;

@@ -1,0 +1,85 @@
+"""Host-side mirror of the reference's `tracs distance` stage for the hot path: one pair sweep per
+MSA (+ optional query-vs-database FASTA), optional TransCluster likelihood from sampling dates, one
+CSV row per kept edge. Same options, column order and quirks as gtonkinhill/tracs
+tracs/distance.py:15-259 (cited inline), written against the drop-in module's entry points so a
+GPU box without the reference checkout can produce byte-comparable CSVs.
+
+The reference's own tracs/distance.py also runs unchanged on top of tracs_b200/dropin/TRACS.py;
+this module exists so the parity tests do not need /root/reference at run time."""
+import argparse
+import os
+from datetime import date
+
+import numpy as np
+
+from . import api
+
+SECONDS_IN_YEAR = 31556952.0  # tracs/transcluster.py:5
+HEADER = ("sampleA,sampleB,date difference,SNP distance,transmission distance,expected K,"
+          "filtered SNP distance,sites considered,MSA file\n")  # tracs/distance.py:156-158
+
+
+def read_dates(path):
+    """tracs/distance.py:145-151: skip the header line; column 0 = sample, column 1 = ISO date."""
+    dates = {}
+    with open(path) as f:
+        next(f)
+        for line in f:
+            parts = line.strip().split(",")
+            dates[parts[0]] = date.fromisoformat(parts[1])
+    return dates
+
+
+def date_differences(rows, cols, names, dates):
+    """tracs/transcluster.py:26-33: seconds since 1970-01-01 for samples 0..max index (KeyError if
+    one has no date), |t_i - t_j| / SECONDS_IN_YEAR."""
+    epoch = date.fromisoformat("1970-01-01")
+    top = int(max(max(rows), max(cols)))
+    t = np.array([(dates[names[s]] - epoch).total_seconds() for s in range(top + 1)])
+    return np.abs(t[np.asarray(rows, dtype=np.int64)] - t[np.asarray(cols, dtype=np.int64)]) / SECONDS_IN_YEAR
+
+
+def distance(msa_files, output_file, msa_db=None, metadata=None, snp_threshold=2147483647, recomb_filter=False,
+             clock_rate=1e-3 * 29903, trans_rate=73.0, trans_threshold=None, precision=0.01, n_cpu=1):
+    dates = read_dates(metadata) if metadata is not None else None
+    with open(output_file, "w") as out:
+        out.write(HEADER)
+        for msa in msa_files:
+            fastas = [msa, msa_db] if msa_db is not None else [msa]
+            rows, cols, snp, names, filt, ncomp = api.pairsnp(fasta=fastas, n_threads=n_cpu, dist=snp_threshold, filter=recomb_filter)
+            ref = os.path.basename(msa).split(".")[0].replace("_combined", "")  # tracs/distance.py:208-209
+            if dates is not None and len(rows) > 0:
+                dt = date_differences(rows, cols, names, dates)
+                # with the filter on, the likelihood is fed the filtered distance (tracs/distance.py:182-192)
+                p0, eK = api.trans_dist(filt if recomb_filter else snp, dt, clock_rate, trans_rate, precision)
+                p0 = np.exp(np.asarray(p0))  # tracs/transcluster.py:38-39
+                filt_col = filt if recomb_filter else ["NA"] * len(rows)  # tracs/distance.py:204
+                for e in range(len(rows)):
+                    if trans_threshold is None or trans_threshold >= eK[e]:  # tracs/distance.py:222
+                        out.write(",".join([names[rows[e]], names[cols[e]], str(dt[e]), str(int(snp[e])), str(p0[e]), str(eK[e]),
+                                            str(filt_col[e]), str(ncomp[e]), ref]) + "\n")
+            else:
+                for e in range(len(rows)):  # tracs/distance.py:239-258
+                    out.write(",".join([names[rows[e]], names[cols[e]], "NA", str(int(snp[e])), "NA", "NA", str(filt[e]), str(ncomp[e]),
+                                        ref]) + "\n")
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="Pairwise SNP and transmission distances (B200)")
+    ap.add_argument("--msa", dest="msa_files", required=True, nargs="+")
+    ap.add_argument("--msa-db", dest="msa_db", default=None)
+    ap.add_argument("--meta", dest="metadata", default=None)
+    ap.add_argument("-o", "--output", dest="output_file", required=True)
+    ap.add_argument("-D", "--snp_threshold", type=int, default=2147483647)
+    ap.add_argument("--filter", dest="recomb_filter", action="store_true")
+    ap.add_argument("--clock_rate", type=float, default=1e-3 * 29903)
+    ap.add_argument("--trans_rate", type=float, default=73.0)
+    ap.add_argument("-K", "--trans_threshold", type=float, default=None)
+    ap.add_argument("--precision", type=float, default=0.01)
+    ap.add_argument("-t", "--threads", dest="n_cpu", type=int, default=1)
+    a = ap.parse_args(argv)
+    distance(**vars(a))
+
+
+if __name__ == "__main__":
+    main()
