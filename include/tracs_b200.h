@@ -56,9 +56,12 @@ typedef struct tracs_stats {
   uint64_t n_edges;
   uint64_t kernel_launches;  /* kernels of this library launched by the call                */
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t n_candidates;     /* pairs that survived the prefilter sweep (0 if it did not run)       */
+  uint64_t swept_wordpairs;  /* 32-site word-pairs the tile kernel actually evaluated               */
   float ms_pack;             /* ASCII -> column masks + N planes (K0a)                      */
   float ms_compact;          /* variable-site selection + bit-plane gather (K0b)            */
   float ms_sweep;            /* pair tile sweep incl. threshold/compaction epilogue (K1)    */
+  float ms_refine;           /* per-pair refinement of prefilter candidates (K1b)           */
   float ms_sort;             /* edge ordering                                               */
   float ms_ncomp;            /* compared-sites kernel (K2)                                  */
   float ms_trans;            /* transmission LUT + gather (K3)                              */
@@ -77,7 +80,7 @@ typedef struct tracs_opts {
   int32_t want_trans;  /* fused transmission likelihood: needs days != NULL                      */
   const int32_t *days; /* host: sampling day number per sample (days since any epoch)            */
   double lamb, beta, threshold_Ek; /* trans_dist args (src/transcluster.hpp:241)                 */
-  int32_t sweep_variant; /* 0 = default kernel; others are tuning variants (bench only)          */
+  int32_t sweep_variant; /* 0 = prefilter + refine when the threshold allows; 1 = always full tile sweep */
   int32_t keep_on_device; /* reserved */
 } tracs_opts_t;
 

@@ -1,0 +1,82 @@
+"""GPU: the CUDA path through the drop-in `TRACS` module and the distance driver against the golden
+fixtures generated from the unmodified reference (tests/golden/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import tracs_b200
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+G = json.load(open(os.path.join(GOLD, "golden.json")))
+
+
+@pytest.mark.parametrize("case", G["pairsnp"], ids=lambda c: c["fasta"])
+def test_golden_pairsnp(case):
+    T = tracs_b200.install_dropin()
+    r = T.pairsnp(fasta=[os.path.join(GOLD, case["fasta"])], n_threads=1, dist=case["dist"], filter=False)
+    assert isinstance(r, tuple) and len(r) == 6 and all(isinstance(x, list) for x in r)
+    assert r[0] == case["rows"] and r[1] == case["cols"] and r[2] == case["d"]
+    assert r[3] == case["names"] and r[4] == case["filt"] and r[5] == case["ncomp"]
+
+
+def test_golden_two_file():
+    T = tracs_b200.install_dropin()
+    case = G["two_file"][0]
+    r = T.pairsnp(fasta=[os.path.join(GOLD, f) for f in case["fasta"]], n_threads=2, dist=case["dist"], filter=False)
+    assert r[0] == case["rows"] and r[1] == case["cols"] and r[2] == case["d"] and r[3] == case["names"] and r[5] == case["ncomp"]
+
+
+@pytest.mark.parametrize("k", range(len(G["trans_dist"]["cases"])))
+def test_golden_trans_dist(k):
+    T = tracs_b200.install_dropin()
+    c = G["trans_dist"]["cases"][k]
+    days = np.array(c["days"])
+    dt = days * 86400.0 / 31556952.0
+    p0, eK = T.trans_dist(np.array(c["N"]), dt, c["lamb"], c["beta"], c["thr"])
+    assert isinstance(p0, list) and isinstance(eK, list)
+    assert np.allclose(p0, c["p0_log"], rtol=1e-6, atol=0)
+    ref_eK = np.array(c["eK"])
+    pos = (days > 0) & np.isfinite(ref_eK)          # delta == 0 is UB in the reference
+    assert np.allclose(np.array(eK)[pos], ref_eK[pos], rtol=1e-6, atol=0)
+    z = days == 0
+    assert np.allclose(np.array(eK)[z], (np.array(c["N"])[z] + 1) * c["beta"] / c["lamb"], rtol=1e-12)
+
+
+def _rows(path):
+    return [ln.rstrip("\n").split(",") for ln in open(path)]
+
+
+@pytest.mark.parametrize("tag,extra", [("meta", dict(metadata=os.path.join(GOLD, "cli_dates.csv"), trans_threshold=100.0)), ("nometa", {})])
+def test_distance_cli_csv(tmp_path, tag, extra):
+    from tracs_b200 import distance
+    out = str(tmp_path / "d.csv")
+    distance.distance([os.path.join(GOLD, "cli_combined.fasta.gz")], out, snp_threshold=40, n_cpu=2, **extra)
+    got, exp = _rows(out), _rows(os.path.join(GOLD, "cli_%s.csv" % tag))
+    assert got[0] == exp[0] and len(got) == len(exp)
+    for g, e in zip(got[1:], exp[1:]):
+        assert g[0] == e[0] and g[1] == e[1] and g[3] == e[3] and g[6] == e[6] and g[7] == e[7] and g[8] == e[8]
+        if tag == "meta":
+            assert g[2] == e[2]
+            assert abs(float(g[4]) - float(e[4])) <= 1e-6 * abs(float(e[4]))
+            if float(e[2]) > 0:
+                assert abs(float(g[5]) - float(e[5])) <= 1e-6 * abs(float(e[5]))
+        else:
+            assert g[2] == "NA" and g[4] == "NA" and g[5] == "NA"
+
+
+def test_reference_kat_csv(tmp_path):
+    # the reference's tests/test_trans_distance.py values, through the whole driver
+    from tracs_b200 import distance
+    out = str(tmp_path / "kat.csv")
+    distance.distance([os.path.join(GOLD, "kat.fasta")], out, metadata=os.path.join(GOLD, "kat_dates.csv"), trans_threshold=10.0,
+                      snp_threshold=5)
+    rows = _rows(out)
+    l1, l2 = rows[1], rows[2]
+    assert abs(float(l1[2]) - 0.002737907006988508) < 1e-6 and abs(float(l2[2]) - 0.002737907006988508) < 1e-6
+    assert int(l1[3]) == 0 and int(l2[3]) == 2
+    assert abs(float(l1[4]) - 0.23794988406662973) < 1e-6 and abs(float(l2[4]) - 0.024467137572328577) < 1e-6
+    assert abs(float(l1[5]) - 2.6335200453700187) < 1e-6 and abs(float(l2[5]) - 7.315670110063259) < 1e-6
+    assert rows[3][:4] == ["seq2", "seq3", "0.0", "1"] and rows[3][6:] == ["NA", "9", "kat"]

@@ -28,6 +28,25 @@ def test_matrix_parity(oracle_mod, n, L, dist):
     _cmp(res, oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4))
 
 
+@pytest.mark.parametrize("n_clusters,dist,expect", [(60, 20, "refine"), (3, 20, "fallback"), (60, 0, "refine"), (3, 2047, "any")])
+def test_prefilter_refine_and_fallback(oracle_mod, n_clusters, dist, expect):
+    # long enough (>= 256 words of variable sites) for the filter-and-refine path to engage
+    s = synth.generate(300, 200_000, p_var=0.06, n_clusters=n_clusters, mu=4, p_N=0.002, p_amb=0.01, seed=41 + n_clusters)
+    res = tracs_b200.pairsnp_matrix(s, dist=dist)
+    st = tracs_b200.last_stats()
+    _cmp(res, oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4))
+    assert st["n_words"] >= 256
+    if expect == "refine":
+        assert st["ms_refine"] > 0 and st["swept_wordpairs"] == st["n_pairs"] * 64
+    elif expect == "fallback":
+        assert st["ms_refine"] == 0 and st["n_candidates"] > 0 and st["swept_wordpairs"] > st["n_pairs"] * 64
+    full = tracs_b200.pairsnp_matrix(s, dist=dist, full_sweep=True)
+    st2 = tracs_b200.last_stats()
+    assert st2["n_candidates"] == 0 and st2["ms_refine"] == 0
+    for k in ("rows", "cols", "dist", "ncomp"):
+        assert full[k].tolist() == res[k].tolist()
+
+
 def test_identical_and_allN(oracle_mod):
     s = synth.generate(40, 500, p_var=0.0, p_N=0.0, gaps=0, seed=3)
     s[7, :] = ord("N")

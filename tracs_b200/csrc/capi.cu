@@ -72,7 +72,12 @@ static void finish_edges(HostEdges &he, const tracs_opts_t &o, uint64_t n, uint6
   out->ncomp = dup_array(he.ncomp);
   out->filt = (uint64_t *)calloc(std::max<size_t>(1, E), sizeof(uint64_t));
   out->seq_length = L;
-  if (o.want_trans && o.days) {
+  if (o.want_trans && o.days && he.has_trans) {
+    out->p0_log = dup_array(he.p0_log);
+    out->eK = dup_array(he.eK);
+    out->datediff = dup_array(he.datediff);
+  } else if (o.want_trans && o.days) {
+    // key table too large for the device-side path: unique (N, delta) keys are collected on the host.
     // tracs/transcluster.py:26-36: seconds since epoch -> |dt| / SECONDS_IN_YEAR -> trans_dist
     std::vector<double> dt(E), p0(E), ek(E);
     std::vector<int32_t> d32(E);

@@ -104,7 +104,10 @@ inline int shard_owner(uint32_t row_block, int world) {
 // host-side edge columns produced by the sweep (sorted by (row, col))
 struct HostEdges {
   std::vector<uint64_t> rows, cols, dist, ncomp;
+  std::vector<double> p0_log, eK, datediff;  // filled when the fused transmission path ran on the device
+  bool has_trans = false;
 };
+const std::vector<double> &lgamma_table(size_t n);
 void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,
                   HostEdges &out, cudaStream_t st);
 

@@ -19,6 +19,7 @@
 #include <stdexcept>
 
 #include "common.cuh"
+#include "trans.cuh"
 
 namespace tracs {
 
@@ -52,15 +53,26 @@ __host__ __device__ inline uint32_t base_mask(uint32_t c) {
 //   thread <-> one 32-site word (32 ASCII bytes) ; loops over a chunk of samples
 //   lut: 256 entries x 32 lanes (lane-private bank => conflict-free byte lookups)
 // ------------------------------------------------------------------------------------------
-constexpr int PACK_THREADS = 256;
+constexpr int PACK_THREADS = 512;
 constexpr int PACK_SCHUNK = 256;
+constexpr int PACK_BATCH = 4;
+// LUT: row c (256 B) holds one 32-bit entry per lane at byte offset lane*4, so the byte address
+// (c << 8) | (lane << 2) is ONE PRMT away from the packed ASCII word and every lane owns a bank.
+// entry = base mask replicated in the four low nibbles | 0xFFFF0000 if the mask is 1111 (N).
+constexpr size_t PACK_SMEM = 256 * 256;
 
-__device__ __forceinline__ uint32_t lut4(const uint32_t *lut_lane, uint32_t w) {
-  uint32_t e0 = lut_lane[(w & 0xFFu) << 5];
-  uint32_t e1 = lut_lane[((w >> 8) & 0xFFu) << 5];
-  uint32_t e2 = lut_lane[((w >> 16) & 0xFFu) << 5];
-  uint32_t e3 = lut_lane[(w >> 24) << 5];
-  return e0 | (e1 << 4) | (e2 << 8) | (e3 << 12);
+// bit-select: (a & m) | (b & ~m)  -> one LOP3
+__device__ __forceinline__ uint32_t bsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
+
+// four ASCII bytes -> low 16 bits: four 4-bit masks ; bits 16-19 and 20-23: the four is-N flags
+__device__ __forceinline__ uint32_t lut4(const char *lut, uint32_t lane4, uint32_t w) {
+  const uint32_t e0 = *reinterpret_cast<const uint32_t *>(lut + __byte_perm(w, lane4, 0x5504));
+  const uint32_t e1 = *reinterpret_cast<const uint32_t *>(lut + __byte_perm(w, lane4, 0x5514));
+  const uint32_t e2 = *reinterpret_cast<const uint32_t *>(lut + __byte_perm(w, lane4, 0x5524));
+  const uint32_t e3 = *reinterpret_cast<const uint32_t *>(lut + __byte_perm(w, lane4, 0x5534));
+  const uint32_t t01 = bsel(e0, e1, 0x00550F0Fu);
+  const uint32_t t23 = bsel(e2, e3, 0x00550F0Fu);
+  return bsel(t01, t23, 0x003300FFu);
 }
 // bit i of result = nibble i of x is 0xF
 __device__ __forceinline__ uint32_t nibbles_all_ones(uint32_t x) {
@@ -76,11 +88,14 @@ __device__ __forceinline__ uint32_t nibbles_all_ones(uint32_t x) {
 __global__ void __launch_bounds__(PACK_THREADS)
 k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
        uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/) {
-  __shared__ uint32_t lut[256 * 32];
-  for (int i = threadIdx.x; i < 256 * 32; i += PACK_THREADS) lut[i] = base_mask(i >> 5);
+  extern __shared__ __align__(256) char lut[];
+  for (int i = threadIdx.x; i < 256 * 32; i += PACK_THREADS) {
+    const uint32_t m = base_mask(i >> 5);
+    *reinterpret_cast<uint32_t *>(lut + ((i >> 5) << 8) + ((i & 31) << 2)) = m * 0x1111u | (m == 15u ? 0xFFFF0000u : 0u);
+  }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t *lut_lane = lut + lane;
+  const uint32_t lane4 = lane << 2;
   const uint64_t w = (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x;  // word index
   const uint64_t s0 = (uint64_t)blockIdx.y * PACK_SCHUNK;
   const uint64_t s1 = min(n, s0 + PACK_SCHUNK);
@@ -91,29 +106,49 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch,
   uint32_t acc0 = ~0u, acc1 = ~0u, acc2 = ~0u, acc3 = ~0u;
   uint32_t valid = 0xFFFFFFFFu;
   if (has_sites && L - site0 < 32) valid = (1u << (uint32_t)(L - site0)) - 1u;
-  for (uint64_t s = s0; s < s1; ++s) {
-    uint32_t isn = 0;
-    if (has_sites) {
-      const uint4 *src = reinterpret_cast<const uint4 *>(seqs + s * pitch + site0);
-      uint4 a = __ldg(src), b = __ldg(src + 1);
-      uint32_t m0 = lut4(lut_lane, a.x) | (lut4(lut_lane, a.y) << 16);
-      uint32_t m1 = lut4(lut_lane, a.z) | (lut4(lut_lane, a.w) << 16);
-      uint32_t m2 = lut4(lut_lane, b.x) | (lut4(lut_lane, b.y) << 16);
-      uint32_t m3 = lut4(lut_lane, b.z) | (lut4(lut_lane, b.w) << 16);
-      isn = nibbles_all_ones(m0) | (nibbles_all_ones(m1) << 8) | (nibbles_all_ones(m2) << 16) |
-            (nibbles_all_ones(m3) << 24);
-      isn &= valid;
-      acc0 &= m0; acc1 &= m1; acc2 &= m2; acc3 &= m3;
+  // PACK_BATCH samples per trip: all global loads of the batch are issued before any table lookup,
+  // so every thread keeps 2 * PACK_BATCH 16-byte loads in flight (the kernel is HBM-latency bound).
+  for (uint64_t sb = s0; sb < s1; sb += PACK_BATCH) {
+    uint4 va[PACK_BATCH], vb[PACK_BATCH];
+#pragma unroll
+    for (int t = 0; t < PACK_BATCH; ++t) {
+      if (has_sites && sb + t < s1) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(seqs + (sb + t) * pitch + site0);
+        va[t] = __ldcs(src);
+        vb[t] = __ldcs(src + 1);
+      } else {
+        va[t] = vb[t] = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);  // 'N': neutral for the column AND
+      }
     }
-    if (in_row) {
-      nplane[s * npitch + w] = isn;
-      // block summary: one bit per 4 words (128 sites), one byte per warp (1024 sites)
-      uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
-      if (lane == 0) {
-        uint32_t t = nz | (nz >> 1);
-        t |= (t >> 2);
-        t &= 0x11111111u;
-        nsum[s * spitch + (w >> 5)] = (uint8_t)nibbles_all_ones(t * 0xFu);
+#pragma unroll
+    for (int t = 0; t < PACK_BATCH; ++t) {
+      const uint64_t s = sb + t;
+      if (s >= s1) break;
+      uint32_t isn = 0;
+      if (has_sites) {
+        const uint4 a = va[t], b = vb[t];
+        const uint32_t x0 = lut4(lut, lane4, a.x), x1 = lut4(lut, lane4, a.y), x2 = lut4(lut, lane4, a.z), x3 = lut4(lut, lane4, a.w);
+        const uint32_t x4 = lut4(lut, lane4, b.x), x5 = lut4(lut, lane4, b.y), x6 = lut4(lut, lane4, b.z), x7 = lut4(lut, lane4, b.w);
+        // eight sites per register: 4-bit masks
+        acc0 &= __byte_perm(x0, x1, 0x5410);
+        acc1 &= __byte_perm(x2, x3, 0x5410);
+        acc2 &= __byte_perm(x4, x5, 0x5410);
+        acc3 &= __byte_perm(x6, x7, 0x5410);
+        // byte 2 of each pair: is-N flags of eight sites
+        const uint32_t n0 = bsel(x0, x1, 0x000F0000u), n1 = bsel(x2, x3, 0x000F0000u);
+        const uint32_t n2 = bsel(x4, x5, 0x000F0000u), n3 = bsel(x6, x7, 0x000F0000u);
+        isn = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n2, n3, 0x0062), 0x5410) & valid;
+      }
+      if (in_row) {
+        __stcs(nplane + s * npitch + w, isn);
+        // block summary: one bit per 4 words (128 sites), one byte per warp (1024 sites)
+        uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
+        if (lane == 0) {
+          uint32_t t2 = nz | (nz >> 1);
+          t2 |= (t2 >> 2);
+          t2 &= 0x11111111u;
+          nsum[s * spitch + (w >> 5)] = (uint8_t)nibbles_all_ones(t2 * 0xFu);
+        }
       }
     }
   }
@@ -167,7 +202,7 @@ __global__ void k_siteflags(const uint32_t *__restrict__ colmask, uint64_t L, ui
 // K0b: bit-slice the variable sites. One warp per (word, sample-chunk); lane <-> site.
 __global__ void __launch_bounds__(256)
 k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uint32_t *__restrict__ site_idx, uint64_t V,
-         uint4 *__restrict__ planes, uint64_t Npad, uint32_t schunk) {
+         uint4 *__restrict__ planes, uint64_t Npad, uint4 *__restrict__ planesT, uint64_t Wp, uint32_t schunk) {
   __shared__ uint8_t lut[256];
   lut[threadIdx.x] = (uint8_t)base_mask(threadIdx.x);
   __syncthreads();
@@ -178,14 +213,26 @@ k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uin
   const bool live = v < V;
   const uint64_t site = live ? site_idx[v] : 0;
   const uint64_t s0 = (uint64_t)blockIdx.y * schunk, s1 = min(n, s0 + schunk);
-#pragma unroll 4
-  for (uint64_t s = s0; s < s1; ++s) {
-    uint32_t m = live ? lut[seqs[s * pitch + site]] : 15u;
-    uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
-    uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
-    uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
-    uint32_t T = __ballot_sync(0xFFFFFFFFu, m & 8);
-    if (lane == 0) planes[w * Npad + s] = make_uint4(A, C, G, T);
+  constexpr int GB = 8;  // byte loads in flight per lane
+  for (uint64_t sb = s0; sb < s1; sb += GB) {
+    uint8_t ch[GB];
+#pragma unroll
+    for (int t = 0; t < GB; ++t) ch[t] = (live && sb + t < s1) ? __ldg(seqs + (sb + t) * pitch + site) : (uint8_t)'N';
+#pragma unroll
+    for (int t = 0; t < GB; ++t) {
+      const uint64_t s = sb + t;
+      if (s >= s1) break;
+      const uint32_t m = live ? lut[ch[t]] : 15u;
+      const uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
+      const uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
+      const uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
+      const uint32_t T = __ballot_sync(0xFFFFFFFFu, m & 8);
+      if (lane == 0) {
+        const uint4 v = make_uint4(A, C, G, T);
+        planes[w * Npad + s] = v;    // word-major: tile panels are contiguous 2 KB rows
+        planesT[s * Wp + w] = v;     // sample-major: per-pair refinement streams rows
+      }
+    }
   }
 }
 
@@ -208,6 +255,7 @@ struct SweepArgs {
   uint64_t *keys;
   uint32_t *dvals;
   unsigned long long cap;
+  uint32_t one;  // == 1, opaque to the compiler: acc += popc * one issues as IMAD on the FMA pipe
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -241,6 +289,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 constexpr int SWEEP_THREADS = 256;
 constexpr int STAGE_U4 = KC * TILE;  // uint4 per stage per side
+constexpr uint32_t PREFILTER_WORDS = 64;  // 2048 variable sites
 constexpr size_t SWEEP_SMEM = (size_t)STAGES * 2 * STAGE_U4 * sizeof(uint4);
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
@@ -258,6 +307,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
   __syncthreads();
 
   const uint32_t nk = a.Wp / KC;
+  const uint32_t one = a.one;
   uint32_t it = 0;  // running chunk counter (stage = it % STAGES, parity = (it / STAGES) & 1)
 
   for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -309,8 +359,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
           const uint4 cv = pc[kk * TILE + j * 16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            uint32_t m = (r[i].x & cv.x) | (r[i].y & cv.y) | (r[i].z & cv.z) | (r[i].w & cv.w);
-            acc[i][j] += __popc(m);
+            const uint32_t m = (r[i].x & cv.x) | (r[i].y & cv.y) | (r[i].z & cv.z) | (r[i].w & cv.w);
+            // accumulate on the FMA pipe (IMAD) so the ALU pipe only carries the four LOP3
+            acc[i][j] = __popc(m) * one + acc[i][j];
           }
         }
       }
@@ -381,6 +432,39 @@ __global__ void k_expand(const uint64_t *__restrict__ keys, const uint32_t *__re
 }
 
 // ------------------------------------------------------------------------------------------
+// K1b: refinement of prefilter candidates. The tile sweep over the first w0 words leaves only pairs
+// whose PARTIAL distance is <= dist (d is monotone in the number of sites, so every other pair is
+// already decided). One warp finishes one candidate over words [w0, Wp) of the sample-major planes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_refine(const uint64_t *__restrict__ ckeys, const uint32_t *__restrict__ cdvals, uint64_t n_cand,
+         const uint4 *__restrict__ planesT, uint32_t Wp, uint32_t w0, int32_t dist, unsigned long long *counter,
+         uint64_t *__restrict__ keys, uint32_t *__restrict__ dvals) {
+  const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (e >= n_cand) return;
+  const uint64_t k = ckeys[e];
+  const uint4 *ri = planesT + (k >> 32) * Wp;
+  const uint4 *rj = planesT + (k & 0xFFFFFFFFull) * Wp;
+  uint32_t mism = 0;
+#pragma unroll 4
+  for (uint32_t w = w0 + lane; w < Wp; w += 32) {
+    const uint4 x = __ldg(ri + w), y = __ldg(rj + w);
+    mism += __popc(~((x.x & y.x) | (x.y & y.y) | (x.z & y.z) | (x.w & y.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mism += __shfl_xor_sync(0xFFFFFFFFu, mism, o);
+  if (lane == 0) {
+    const uint32_t d = cdvals[e] + mism;
+    if ((int32_t)d <= dist) {
+      const unsigned long long pos = atomicAdd(counter, 1ull);
+      keys[pos] = k;
+      dvals[pos] = d;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K2: compared sites. nn = L - |N_i u N_j| = L - (|N_i| + |N_j| - |N_i n N_j|).
 // The intersection walks the block summaries (1 bit / 128 sites) and touches the N-plane only
 // where BOTH samples have an N in the block. One warp per edge.
@@ -413,6 +497,43 @@ k_ncomp(const uint64_t *__restrict__ keys, uint64_t E, const uint32_t *__restric
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) inter += __shfl_xor_sync(0xFFFFFFFFu, inter, o);
   if (lane == 0) ncomp[e] = L - ((uint64_t)ncount[i] + ncount[j] - inter);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (fused): transmission likelihood for the emitted edges, all on the device.
+// Dates have day resolution (tracs/transcluster.py:26-33), so the memo key (N, delta) of
+// src/transcluster.hpp:245-274 is (d, |day_i - day_j|): a dense table indexed d * DD + dd.
+//   mark used keys -> compact -> one thread per used key runs the series -> per-edge gather
+// ------------------------------------------------------------------------------------------
+__global__ void k_trans_mark(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ dvals, uint64_t E,
+                             const int32_t *__restrict__ days, uint32_t DD, uint8_t *__restrict__ used) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const uint64_t k = keys[e];
+  const int32_t dd = abs(days[k >> 32] - days[k & 0xFFFFFFFFull]);
+  used[(uint64_t)dvals[e] * DD + (uint32_t)dd] = 1;
+}
+__global__ void k_trans_table(const uint32_t *__restrict__ key_idx, const uint64_t *__restrict__ n_keys, uint32_t DD,
+                              const double *__restrict__ lg, double lamb, double beta, double thr,
+                              double *__restrict__ p0_lut, double *__restrict__ eK_lut) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *n_keys) return;
+  const uint32_t id = key_idx[t];
+  const double delta = ((double)(id % DD) * 86400.0) / 31556952.0;  // == |t_i - t_j| / SECONDS_IN_YEAR
+  trans_eval((int64_t)(id / DD), delta, lg, lamb, beta, thr, &p0_lut[id], &eK_lut[id]);
+}
+__global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ dvals, uint64_t E,
+                               const int32_t *__restrict__ days, uint32_t DD, const double *__restrict__ p0_lut,
+                               const double *__restrict__ eK_lut, double *__restrict__ p0, double *__restrict__ eK,
+                               double *__restrict__ dt) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const uint64_t k = keys[e];
+  const int32_t dd = abs(days[k >> 32] - days[k & 0xFFFFFFFFull]);
+  const uint64_t id = (uint64_t)dvals[e] * DD + (uint32_t)dd;
+  p0[e] = p0_lut[id];
+  eK[e] = eK_lut[id];
+  dt[e] = ((double)dd * 86400.0) / 31556952.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -453,7 +574,12 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   TRACS_CK(cudaMemsetAsync(nsum.p, 0, nsum.n, st));
   if (L > 0) {
     dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((n + PACK_SCHUNK - 1) / PACK_SCHUNK));
-    k_pack<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch);
+    static bool pack_attr = false;
+    if (!pack_attr) {
+      TRACS_CK(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PACK_SMEM));
+      pack_attr = true;
+    }
+    k_pack<<<grid, PACK_THREADS, PACK_SMEM, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch);
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
     if (want_n) {
@@ -490,12 +616,13 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   const uint32_t Npad = (uint32_t)round_up(n, TILE);
   S.n_variable_sites = V;
   S.n_words = Wp;
-  DevBuf<uint4> planes((size_t)Wp * Npad);
+  DevBuf<uint4> planes((size_t)Wp * Npad), planesT((size_t)Wp * n);
   TRACS_CK(cudaMemsetAsync(planes.p, 0xFF, planes.n * sizeof(uint4), st));
+  TRACS_CK(cudaMemsetAsync(planesT.p, 0xFF, planesT.n * sizeof(uint4), st));
   if (W > 0) {
     const uint32_t schunk = 512;
     dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
-    k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, planes.p, Npad, schunk);
+    k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, planes.p, Npad, planesT.p, Wp, schunk);
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
   }
@@ -575,6 +702,43 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, SWEEP_THREADS, SWEEP_SMEM);
   occ = std::max(1, occ);
 
+  // ---- fused transmission likelihood set-up (device table over (d, day difference)) ----------
+  bool fuse_trans = false;
+  uint32_t DD = 0;
+  uint64_t lut_size = 0;
+  DevBuf<int32_t> d_days;
+  DevBuf<double> d_lg, p0_lut, eK_lut;
+  DevBuf<uint8_t> used;
+  DevBuf<uint32_t> key_idx;
+  DevBuf<uint64_t> n_keys;
+  DevBuf<uint8_t> sel_tmp;
+  size_t sel_tmp_bytes = 0;
+  if (o.want_trans && o.days) {
+    int32_t dmin = o.days[0], dmaxday = o.days[0];
+    for (uint64_t s = 0; s < n; ++s) {
+      dmin = std::min(dmin, o.days[s]);
+      dmaxday = std::max(dmaxday, o.days[s]);
+    }
+    const uint64_t dd_span = (uint64_t)((int64_t)dmaxday - (int64_t)dmin) + 1;
+    const uint64_t d_top = (uint64_t)std::min<int64_t>(std::max<int64_t>(o.dist, 0), (int64_t)Wp * 32) + 1;
+    if (o.dist >= 0 && dd_span * d_top <= (1ull << 24)) {
+      fuse_trans = true;
+      DD = (uint32_t)dd_span;
+      lut_size = dd_span * d_top;
+      d_days.alloc(n);
+      TRACS_CK(cudaMemcpyAsync(d_days.p, o.days, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      const size_t nlg = (size_t)d_top + 10000 + 8;
+      const std::vector<double> &lg = lgamma_table(nlg);
+      d_lg.alloc(nlg);
+      TRACS_CK(cudaMemcpyAsync(d_lg.p, lg.data(), nlg * 8, cudaMemcpyHostToDevice, st));
+      p0_lut.alloc(lut_size); eK_lut.alloc(lut_size); used.alloc(lut_size); key_idx.alloc(lut_size); n_keys.alloc(1);
+      cub::CountingInputIterator<uint32_t> cnt_it(0);
+      cub::DeviceSelect::Flagged(nullptr, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
+      sel_tmp.alloc(sel_tmp_bytes);
+      out.has_trans = true;
+    }
+  }
+
   for (size_t b = 0; b < bands.size(); ++b) {
     std::vector<uint32_t> rbs(my_rb.begin() + bands[b].first, my_rb.begin() + bands[b].second);
     std::vector<uint32_t> prefix(rbs.size() + 1, 0);
@@ -588,17 +752,61 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     a.planes = planes.p; a.Wp = Wp; a.Npad = Npad; a.n = (uint32_t)n; a.i_end = (uint32_t)i_end;
     a.j_start = (uint32_t)j_start; a.dist = o.dist; a.rb_list = d_rb.p; a.tile_prefix = d_prefix.p;
     a.n_rb = (uint32_t)rbs.size(); a.n_tiles = n_tiles; a.cb_min = cb_min; a.counter = counter.p;
-    a.keys = keys.p; a.dvals = dv.p; a.cap = cap;
-    T.start();
+    a.keys = keys.p; a.dvals = dv.p; a.cap = cap; a.one = 1;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)n_sm * occ);
-    k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
-    S.kernel_launches++;
-    TRACS_CK(cudaGetLastError());
-    S.ms_sweep += T.stop();
-
+    auto read_counter = [&]() -> unsigned long long {
+      unsigned long long c = 0;
+      TRACS_CK(cudaMemcpyAsync(&c, counter.p, sizeof c, cudaMemcpyDeviceToHost, st));
+      TRACS_CK(cudaStreamSynchronize(st));
+      return c;
+    };
+    // Filter-and-refine for thresholded sweeps: tile-sweep only the first PREFILTER_WORDS words; a
+    // pair whose partial distance already exceeds `dist` is decided. If few pairs survive, finish
+    // those per pair (k_refine); otherwise fall back to the full-length tile sweep.
     unsigned long long E = 0;
-    TRACS_CK(cudaMemcpyAsync(&E, counter.p, sizeof E, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaStreamSynchronize(st));
+    bool refined = false;
+    const bool try_prefilter = o.sweep_variant != 1 && o.dist >= 0 && (uint64_t)o.dist < (uint64_t)PREFILTER_WORDS * 32 &&
+                               Wp >= 4 * PREFILTER_WORDS;
+    if (try_prefilter) {
+      a.Wp = PREFILTER_WORDS;
+      T.start();
+      k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
+      S.kernel_launches++;
+      TRACS_CK(cudaGetLastError());
+      S.ms_sweep += T.stop();
+      S.swept_wordpairs += band_pairs[b] * PREFILTER_WORDS;
+      const unsigned long long n_cand = read_counter();
+      if (n_cand > cap) throw std::runtime_error("internal error: edge buffer overflow");
+      S.n_candidates += n_cand;
+      if (n_cand * 25 <= band_pairs[b]) {  // <= 4 % survive: per-pair refinement is cheaper than tiles
+        refined = true;
+        TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+        if (n_cand) {
+          T.start();
+          k_refine<<<(unsigned)((n_cand * 32 + 255) / 256), 256, 0, st>>>(keys.p, dv.p, n_cand, planesT.p, Wp, PREFILTER_WORDS, o.dist,
+                                                                       counter.p, keys2.p, dv2.p);
+          S.kernel_launches++;
+          TRACS_CK(cudaGetLastError());
+          S.ms_refine += T.stop();
+          E = read_counter();
+        }
+        std::swap(keys.p, keys2.p);  // survivors now in (keys, dv) like the plain sweep leaves them
+        std::swap(dv.p, dv2.p);
+      } else {
+        TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+      }
+    }
+    if (!refined) {
+      a.Wp = Wp;
+      a.keys = keys.p; a.dvals = dv.p;
+      T.start();
+      k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
+      S.kernel_launches++;
+      TRACS_CK(cudaGetLastError());
+      S.ms_sweep += T.stop();
+      S.swept_wordpairs += band_pairs[b] * std::max<uint64_t>(W, 1);  // algorithmic words (padding not counted)
+      E = read_counter();
+    }
     if (E > cap) throw std::runtime_error("internal error: edge buffer overflow");
     if (E == 0) continue;
 
@@ -618,7 +826,30 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       TRACS_CK(cudaGetLastError());
       S.ms_ncomp += T.stop();
     }
+    DevBuf<double> d_p0, d_eK, d_dt;
+    if (fuse_trans) {
+      T.start();
+      d_p0.alloc(E); d_eK.alloc(E); d_dt.alloc(E);
+      TRACS_CK(cudaMemsetAsync(used.p, 0, lut_size, st));
+      k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dv2.p, E, d_days.p, DD, used.p);
+      cub::CountingInputIterator<uint32_t> cnt_it(0);
+      cub::DeviceSelect::Flagged(sel_tmp.p, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
+      k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, st>>>(key_idx.p, n_keys.p, DD, d_lg.p, o.lamb, o.beta, o.threshold_Ek,
+                                                                    p0_lut.p, eK_lut.p);
+      k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dv2.p, E, d_days.p, DD, p0_lut.p, eK_lut.p, d_p0.p,
+                                                                 d_eK.p, d_dt.p);
+      S.kernel_launches += 5;
+      TRACS_CK(cudaGetLastError());
+      S.ms_trans += T.stop();
+    }
     const size_t old = out.rows.size();
+    if (fuse_trans) {
+      out.p0_log.resize(old + E); out.eK.resize(old + E); out.datediff.resize(old + E);
+      TRACS_CK(cudaMemcpyAsync(out.p0_log.data() + old, d_p0.p, E * 8, cudaMemcpyDeviceToHost, st));
+      TRACS_CK(cudaMemcpyAsync(out.eK.data() + old, d_eK.p, E * 8, cudaMemcpyDeviceToHost, st));
+      TRACS_CK(cudaMemcpyAsync(out.datediff.data() + old, d_dt.p, E * 8, cudaMemcpyDeviceToHost, st));
+      S.d2h_bytes += E * 24;
+    }
     out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E); out.ncomp.resize(old + E, 0);
     TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));

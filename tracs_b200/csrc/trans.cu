@@ -21,61 +21,28 @@
 #include <vector>
 
 #include "common.cuh"
+#include "trans.cuh"
 
 namespace tracs {
-
-__device__ __forceinline__ double lae(double x, double y) {
-  // transcluster.hpp:62-75
-  const double t = x - y;
-  if (x == y) return x + 0.69314718055994530942;
-  if (t > 0) return x + log1p(exp(-t));
-  else if (t <= 0) return y + log1p(exp(t));
-  return t;
-}
 
 __global__ void k_trans_keys(const int32_t *__restrict__ keyN, const double *__restrict__ keyD, uint32_t n_keys,
                              const double *__restrict__ lg, double lamb, double beta, double thr,
                              double *__restrict__ p0_log, double *__restrict__ eK) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_keys) return;
-  const int64_t N = keyN[t];
-  const double delta = keyD[t];
-  const double ln_l = log(lamb), ln_b = log(beta), ln_lb = log(lamb + beta);
-  if (!(delta > 0)) {
-    // transcluster.hpp:163-167 with k = 0 ; E[K] see header
-    p0_log[t] = (double)(N + 1) * ln_l + lg[N + 1] - lg[N + 1] - lg[1] - (double)(N + 1) * ln_lb;
-    eK[t] = (double)(N + 1) * beta / lamb;
-    return;
+  trans_eval(keyN[t], keyD[t], lg, lamb, beta, thr, &p0_log[t], &eK[t]);
+}
+
+// lg[x] = lgamma(x) by the host libm, like the reference's table (transcluster.hpp:253-258) but long
+// enough that k < 10000 never reads past it. Cached across calls.
+const std::vector<double> &lgamma_table(size_t n) {
+  static std::vector<double> lg;
+  if (lg.size() < n) {
+    size_t old = lg.size();
+    lg.resize(n);
+    for (size_t i = old; i < n; ++i) lg[i] = ::lgamma((double)i);
   }
-  const double ln_ld = log(lamb * delta);
-  const double ln_d = log(delta);
-  double pois = -INFINITY;
-  for (int64_t i = 0; i <= N; ++i) pois = lae((double)i * ln_ld - lg[i + 1], pois);
-  // G_M for M = N
-  const double lx = ln_d + ln_lb;
-  double G = -INFINITY;
-  for (int64_t j = 0; j <= N; ++j) G = lae((double)j * lx - lg[j + 1], G);
-  const double common = (double)(N + 1) * ln_l - lg[N + 1] - delta * beta - pois;
-  // k = 0 : p0
-  {
-    const double lhs = common + lg[N + 1] - lg[1];
-    p0_log[t] = lhs + (G - (double)(N + 1) * ln_lb);
-  }
-  const double ub = exp(ln_b + delta * lamb + log((double)(N + 1)) - (ln_l + pois));
-  double lprob = -INFINITY, elprob = -INFINITY, diff = thr + 1.0;
-  int64_t k = 1;
-  while (!(diff <= thr) && k < 10000) {
-    const int64_t M = N + k;
-    G = lae((double)M * lx - lg[M + 1], G);
-    const double lhs = common + (double)k * ln_b + lg[M + 1] - lg[k + 1];
-    const double lp = lhs + (G - (double)(M + 1) * ln_lb);
-    const double lk = log((double)k);
-    lprob = lae(lprob, lp + lk);
-    elprob = lae(elprob, lhs + lk + delta * (lamb + beta) - (double)(M + 1) * ln_lb);
-    diff = ub - exp(elprob);
-    ++k;
-  }
-  eK[t] = exp(lprob);
+  return lg;
 }
 
 namespace {
@@ -114,8 +81,7 @@ void trans_dist_device(const int32_t *snp, const double *dt, size_t n, double la
   const uint32_t nk = (uint32_t)kN.size();
   // lg[x] = lgamma(x), host libm like the reference (transcluster.hpp:253-258), long enough for k < 10000
   const size_t nlg = (size_t)maxN + 10000 + 8;
-  std::vector<double> lg(nlg);
-  for (size_t i = 0; i < nlg; ++i) lg[i] = ::lgamma((double)i);
+  const std::vector<double> &lg = lgamma_table(nlg);
   DevBuf<double> d_lg(nlg), d_kD(nk), d_p0(nk), d_eK(nk);
   DevBuf<int32_t> d_kN(nk);
   Timer T(st);
