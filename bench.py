@@ -12,8 +12,11 @@ likelihood with sampling dates (SURVEY 8d "C2").
   value         P*L / step time, inputs resident in HBM (device-generated synthetic ASCII).
   e2e           same metric through the C-ABI call that takes a HOST buffer (tracs_pairsnp_host):
                 H2D copy of the 50 GB ASCII matrix and D2H of the edge list inside the timed region.
-  --gpus N      strong scaling: the same alignment on every rank, triangle row-blocks dealt
-                boustrophedon across ranks, edge lists gathered to rank 0 over NCCL.
+  --gpus N      weak scaling over independent objects: one C2-shaped MSA (one reference genome's
+                alignment, distinct seed) per GPU -- the loop `for msa in args.msa_files` of
+                tracs/distance.py:159 -- no traffic during the sweep, per-MSA edge lists gathered to
+                rank 0 over NCCL inside the timed step. (--shard tiles: strong scaling of ONE alignment
+                by triangle row-blocks, ingest replicated.)
   --impl reference   the unmodified reference (oracle/_ref, built from /root/reference/src) timed on
                 the host cores on a bounded sample of the same workload.
 """
@@ -124,7 +127,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "site-pair comparisons/s (P*L/t)", "value": val, "unit": "site-pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 bitset words", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitset words", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"], "sample": smp.desc},
         "cpu_baseline": {"value": val, "unit": "site-pairs/s", "cores": cores, "kind": kind, "sample": smp.desc, "what": what,
                          "pair_stage_site_pairs_per_s": float(np.median([r["pair_rate"] for r in rs])),
@@ -198,6 +201,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--shard", default="msa", choices=["msa", "tiles"], help="N>1: one MSA per GPU (weak) or row-blocks of one MSA (strong)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -234,18 +238,20 @@ def main():
     # ---- synthetic input, generated in device memory ------------------------------------------
     seqs = torch.empty(n * pitch, dtype=torch.uint8, device=device)
     d_days = torch.empty(n, dtype=torch.int32, device=device)
-    tracs_b200.synth_device(seqs.data_ptr(), n, L, pitch, seed=w["seed"], p_var=w["p_var"], n_clusters=w["n_clusters"], mu=w["mu"],
+    by_tiles = world > 1 and args.shard == "tiles"
+    my_seed = w["seed"] if (world == 1 or by_tiles) else w["seed"] + 1000 * rank
+    tracs_b200.synth_device(seqs.data_ptr(), n, L, pitch, seed=my_seed, p_var=w["p_var"], n_clusters=w["n_clusters"], mu=w["mu"],
                             p_N=w["p_N"], p_amb=w["p_amb"], gc=w["gc"], n_days=w["n_days"], gaps=w["gaps"], dev_days=d_days.data_ptr())
     days = d_days.cpu().numpy()
     kw = dict(dist=w["dist"], days=days, lamb=w["lamb"], beta=w["beta"], threshold_Ek=w["threshold_Ek"],
-              shard_rank=rank, shard_world=world)
+              shard_rank=rank if by_tiles else 0, shard_world=world if by_tiles else 1)
 
     peak = tracs_b200.int_peak() if rank == 0 else None
 
     def step():
-        res = tracs_b200.pairsnp_device(seqs.data_ptr(), n, L, pitch, **kw)
+        res = tracs_b200.pairsnp_device(seqs.data_ptr(), n, L, pitch, copy=False, **kw)
         st = tracs_b200.last_stats()
-        merged = gather_edges(res, rank, world, dist_mod, torch, device) if world > 1 else res
+        merged = gather_edges(res, rank, world, dist_mod, torch, device, merge=by_tiles) if world > 1 else res
         return res, st, merged
 
     def sync():
@@ -277,7 +283,8 @@ def main():
         dist_mod.all_reduce(t_ms, op=dist_mod.ReduceOp.MAX)
     ms = float(t_ms.item())
     ms_per_step = ms / args.steps
-    value = P * L / (ms_per_step * 1e-3)
+    n_msa = 1 if (world == 1 or by_tiles) else world
+    value = n_msa * P * L / (ms_per_step * 1e-3)
 
     def avg(k):
         return float(np.mean([s[k] for s in stats]))
@@ -285,7 +292,12 @@ def main():
     line = None
     if rank == 0:
         st = stats[-1]
-        n_edges = len(merged["rows"]) if isinstance(merged, dict) else merged.shape[1]
+        if isinstance(merged, dict):
+            n_edges = len(merged["rows"])
+        elif isinstance(merged, list):
+            n_edges = int(sum(p.shape[1] for p in merged))
+        else:
+            n_edges = merged.shape[1]
         launches = int(sum(s["kernel_launches"] for s in stats))
         # ---- rooflines ---------------------------------------------------------------------------
         # k_sweep (INT-pipe bound): algorithmic work = 6 INT instructions per 32-site word-pair
@@ -331,15 +343,17 @@ def main():
         roof_full["edges_equal_default_path"] = bool(np.array_equal(res_full["rows"], res["rows"]) and np.array_equal(res_full["cols"], res["cols"])
                                                      and np.array_equal(res_full["dist"], res["dist"]))
         roof = roof_pack if avg("ms_pack") >= avg("ms_sweep") else roof_sweep
-        stages = {k: avg(k) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_total")}
+        stages = {k: avg(k) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_d2h", "ms_total")}
         stages["n_candidates"] = avg("n_candidates")
         line = {
             "metric": "site-pair comparisons/s (P*L/t)", "value": value, "unit": "site-pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if by_tiles else "weak", "vs_baseline": None,
             "dtype": "u32 bit-planes (int32 counts), f64 likelihood", "data": "synthetic (device-generated ASCII alignment, seeded)",
             "config": {"workload": w["name"], "n": n, "L": L, "pairs": P, "variable_sites": int(st["n_variable_sites"]),
                        "words": int(st["n_words"]), "edges": int(n_edges), "dist": w["dist"],
-                       "parallelism": "triangle row-blocks dealt boustrophedon over %d GPU(s); ingest replicated" % world,
+                       "msas": n_msa,
+                       "parallelism": ("triangle row-blocks of one MSA dealt boustrophedon over %d GPUs; ingest replicated" % world) if by_tiles
+                       else ("%d independent MSA(s), one per GPU (tracs/distance.py:159 loop); edge lists gathered to rank 0" % world),
                        "l2": "inputs (%.1f GB ASCII) larger than L2; no flush needed" % (n * pitch / 1e9)},
             "clocks": clk, "gpu_launches": launches, "roofline": roof,
             "roofline_kernels": {"k_pack": roof_pack, "k_sweep": roof_sweep, "k_sweep_full_length": roof_full}, "stages_ms": stages,
@@ -371,7 +385,7 @@ def main():
             def e2e_step():
                 e = _lib.Edges()
                 _lib.check(_lib.lib().tracs_pairsnp_host(hp.ctypes.data, n, L, L, C.byref(o), C.byref(e)))
-                return _lib.take_edges(e, names=False)
+                return _lib.take_edges(e, names=False, copy=False)
 
             e2e_step()
             torch.cuda.synchronize()

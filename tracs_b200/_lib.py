@@ -24,7 +24,7 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("n_samples", "seq_length", "n_variable_sites", "n_words", "n_tiles", "n_pairs",
                                           "n_edges", "kernel_launches", "h2d_bytes", "d2h_bytes", "n_candidates",
                                           "swept_wordpairs")] + \
-               [(k, C.c_float) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_total")]
+               [(k, C.c_float) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_total", "ms_d2h")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -105,20 +105,46 @@ def last_stats():
     return s.as_dict()
 
 
-def take_edges(e, as_lists=False, names=True):
-    """Copies a tracs_edges_t into numpy arrays (or Python lists) and frees it."""
+class _EdgeOwner:
+    """Keeps a tracs_edges_t alive while zero-copy numpy views of its columns exist."""
+
+    def __init__(self, e):
+        self.e = e
+
+    def __del__(self):
+        try:
+            lib().tracs_edges_free(C.byref(self.e))
+        except Exception:
+            pass
+
+
+class EdgeTable(dict):
+    """dict of edge columns; with copy=False the arrays are views into library-owned memory that
+    stays valid as long as this object is alive."""
+    _owner = None
+
+
+def take_edges(e, as_lists=False, names=True, copy=True):
+    """tracs_edges_t -> EdgeTable of numpy arrays (or Python lists). copy=True copies and frees the
+    struct at once; copy=False wraps the library's buffers without copying."""
     n = e.n_edges
 
     def arr(p, dt):
         if not p:
             return None
-        return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        if not n:
+            return np.zeros(0, dt)
+        a = np.ctypeslib.as_array(p, shape=(n,))
+        return a.astype(dt, copy=True) if copy else a
 
-    out = {"rows": arr(e.rows, np.uint64), "cols": arr(e.cols, np.uint64), "dist": arr(e.dist, np.uint64),
-           "filt": arr(e.filt, np.uint64), "ncomp": arr(e.ncomp, np.uint64), "p0_log": arr(e.p0_log, np.float64),
-           "eK": arr(e.eK, np.float64), "datediff": arr(e.datediff, np.float64), "seq_length": int(e.seq_length),
-           "names": [e.names[i].decode() for i in range(e.n_names)] if (names and e.names) else []}
-    lib().tracs_edges_free(C.byref(e))
+    out = EdgeTable({"rows": arr(e.rows, np.uint64), "cols": arr(e.cols, np.uint64), "dist": arr(e.dist, np.uint64),
+                     "filt": arr(e.filt, np.uint64), "ncomp": arr(e.ncomp, np.uint64), "p0_log": arr(e.p0_log, np.float64),
+                     "eK": arr(e.eK, np.float64), "datediff": arr(e.datediff, np.float64), "seq_length": int(e.seq_length),
+                     "names": [e.names[i].decode() for i in range(e.n_names)] if (names and e.names) else []})
+    if copy:
+        lib().tracs_edges_free(C.byref(e))
+    else:
+        out._owner = _EdgeOwner(e)
     if as_lists:
         for k in ("rows", "cols", "dist", "filt", "ncomp"):
             out[k] = out[k].tolist()

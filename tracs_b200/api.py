@@ -83,7 +83,7 @@ def make_opts(dist=INT32_MAX, i_end=0, j_start=0, shard_rank=0, shard_world=1, w
     return o, keep
 
 
-def pairsnp_matrix(seqs, **kw):
+def pairsnp_matrix(seqs, copy=True, **kw):
     """Pair sweep on a HOST ASCII matrix uint8[n][L] (the bytes load_seqs holds per record);
     H2D copy included. Returns a dict of numpy arrays (rows, cols, dist, ncomp[, p0_log, eK, datediff])."""
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
@@ -91,15 +91,15 @@ def pairsnp_matrix(seqs, **kw):
     o, keep = make_opts(**kw)
     e = Edges()
     _lib.check(_lib.lib().tracs_pairsnp_host(seqs.ctypes.data, n, L, L, C.byref(o), C.byref(e)))
-    return _lib.take_edges(e, names=False)
+    return _lib.take_edges(e, names=False, copy=copy)
 
 
-def pairsnp_device(dev_ptr, n, L, pitch, **kw):
+def pairsnp_device(dev_ptr, n, L, pitch, copy=True, **kw):
     """Pair sweep on a DEVICE-resident ASCII matrix (raw device pointer as int)."""
     o, keep = make_opts(**kw)
     e = Edges()
     _lib.check(_lib.lib().tracs_pairsnp_device(C.c_void_p(dev_ptr), n, L, pitch, C.byref(o), C.byref(e)))
-    return _lib.take_edges(e, names=False)
+    return _lib.take_edges(e, names=False, copy=copy)
 
 
 def min_over_refs(a, b, val):

@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <functional>
 #include <numeric>
+#include <mutex>
 #include <stdexcept>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -27,6 +29,77 @@ void pool_init() {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   done_for = dev;
+}
+
+// ---- page-locked host block cache ----------------------------------------------------------------
+namespace {
+struct HostPool {
+  std::mutex mu;
+  std::unordered_map<void *, size_t> live;             // block -> size class (bytes)
+  std::unordered_map<size_t, std::vector<void *>> idle;  // size class -> cached blocks
+  size_t cached_bytes = 0;
+};
+HostPool &host_pool() {
+  static HostPool *hp = new HostPool();  // leaked on purpose: outlives static destructors / CUDA teardown
+  return *hp;
+}
+constexpr size_t HOST_POOL_MIN = 1 << 16;         // smaller requests use malloc
+constexpr size_t HOST_POOL_MAX_CACHED = 8ull << 30;
+}  // namespace
+
+void *host_pool_alloc(size_t bytes) {
+  if (bytes < HOST_POOL_MIN) {
+    void *p = malloc(std::max<size_t>(bytes, 8));
+    if (!p) throw std::bad_alloc();
+    return p;
+  }
+  size_t cls = HOST_POOL_MIN;
+  while (cls < bytes) cls <<= 1;
+  HostPool &hp = host_pool();
+  {
+    std::lock_guard<std::mutex> g(hp.mu);
+    auto it = hp.idle.find(cls);
+    if (it != hp.idle.end() && !it->second.empty()) {
+      void *p = it->second.back();
+      it->second.pop_back();
+      hp.cached_bytes -= cls;
+      hp.live[p] = cls;
+      return p;
+    }
+  }
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, cls, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    p = malloc(cls);  // still correct, just a slower copy
+    if (!p) throw std::bad_alloc();
+    return p;
+  }
+  std::lock_guard<std::mutex> g(hp.mu);
+  hp.live[p] = cls;
+  return p;
+}
+
+void host_pool_free(void *p) {
+  if (!p) return;
+  HostPool &hp = host_pool();
+  {
+    std::lock_guard<std::mutex> g(hp.mu);
+    auto it = hp.live.find(p);
+    if (it == hp.live.end()) {
+      // not a pool block
+    } else {
+      const size_t cls = it->second;
+      hp.live.erase(it);
+      if (hp.cached_bytes + cls <= HOST_POOL_MAX_CACHED) {
+        hp.idle[cls].push_back(p);
+        hp.cached_bytes += cls;
+      } else {
+        cudaFreeHost(p);
+      }
+      return;
+    }
+  }
+  free(p);
 }
 
 static void require_device() {
@@ -57,7 +130,7 @@ static int guarded(F &&f) {
 
 template <typename T>
 static T *dup_array(const std::vector<T> &v) {
-  T *p = (T *)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+  T *p = (T *)host_pool_alloc(std::max<size_t>(1, v.size()) * sizeof(T));
   if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
   return p;
 }
@@ -66,16 +139,17 @@ static void finish_edges(HostEdges &he, const tracs_opts_t &o, uint64_t n, uint6
                          cudaStream_t st) {
   const size_t E = he.rows.size();
   out->n_edges = E;
-  out->rows = dup_array(he.rows);
-  out->cols = dup_array(he.cols);
-  out->dist = dup_array(he.dist);
-  out->ncomp = dup_array(he.ncomp);
-  out->filt = (uint64_t *)calloc(std::max<size_t>(1, E), sizeof(uint64_t));
+  out->filt = (uint64_t *)host_pool_alloc(std::max<size_t>(1, E) * sizeof(uint64_t));
+  memset(out->filt, 0, std::max<size_t>(1, E) * sizeof(uint64_t));
   out->seq_length = L;
+  if (he.ncomp.size() != E) {  // compared sites not requested: zeros
+    he.ncomp.resize(E);
+    if (E) memset(he.ncomp.data(), 0, E * sizeof(uint64_t));
+  }
   if (o.want_trans && o.days && he.has_trans) {
-    out->p0_log = dup_array(he.p0_log);
-    out->eK = dup_array(he.eK);
-    out->datediff = dup_array(he.datediff);
+    out->p0_log = he.p0_log.release();
+    out->eK = he.eK.release();
+    out->datediff = he.datediff.release();
   } else if (o.want_trans && o.days) {
     // key table too large for the device-side path: unique (N, delta) keys are collected on the host.
     // tracs/transcluster.py:26-36: seconds since epoch -> |dt| / SECONDS_IN_YEAR -> trans_dist
@@ -91,6 +165,10 @@ static void finish_edges(HostEdges &he, const tracs_opts_t &o, uint64_t n, uint6
     out->eK = dup_array(ek);
     out->datediff = dup_array(dt);
   }
+  out->rows = he.rows.release();
+  out->cols = he.cols.release();
+  out->dist = he.dist.release();
+  out->ncomp = he.ncomp.release();
   (void)n;
 }
 
@@ -240,8 +318,8 @@ int tracs_set_device(int device) {
 
 void tracs_edges_free(tracs_edges_t *e) {
   if (!e) return;
-  free(e->rows); free(e->cols); free(e->dist); free(e->filt); free(e->ncomp);
-  free(e->p0_log); free(e->eK); free(e->datediff);
+  host_pool_free(e->rows); host_pool_free(e->cols); host_pool_free(e->dist); host_pool_free(e->filt); host_pool_free(e->ncomp);
+  host_pool_free(e->p0_log); host_pool_free(e->eK); host_pool_free(e->datediff);
   if (e->names) {
     for (size_t i = 0; i < e->n_names; ++i) free(e->names[i]);
     free(e->names);
@@ -522,6 +600,12 @@ int tracs_trim(void) {
     TRACS_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     TRACS_CK(cudaDeviceSynchronize());
     TRACS_CK(cudaMemPoolTrimTo(pool, 0));
+    HostPool &hp = host_pool();
+    std::lock_guard<std::mutex> g(hp.mu);
+    for (auto &kv : hp.idle)
+      for (void *p : kv.second) cudaFreeHost(p);
+    hp.idle.clear();
+    hp.cached_bytes = 0;
   });
 }
 

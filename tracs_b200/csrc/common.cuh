@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -102,9 +105,48 @@ inline int shard_owner(uint32_t row_block, int world) {
 }
 
 // host-side edge columns produced by the sweep (sorted by (row, col))
+// Result columns live in page-locked host blocks that are cached across calls (host_pool_*):
+// the D2H copy runs at full PCIe rate into memory that is already mapped, and
+// tracs_edges_free() hands the blocks back to the cache instead of the OS.
+void *host_pool_alloc(size_t bytes);
+void host_pool_free(void *p);
+
+// pool-backed growable column: the D2H copy lands in the buffer that is handed to the caller
+// (tracs_edges_t owns it afterwards), no zero-fill, no second host copy.
+template <typename T>
+struct HostCol {
+  T *p = nullptr;
+  size_t n = 0, cap = 0;
+  HostCol() {}
+  HostCol(const HostCol &) = delete;
+  HostCol &operator=(const HostCol &) = delete;
+  ~HostCol() { host_pool_free(p); }
+  size_t size() const { return n; }
+  T *data() { return p; }
+  T &operator[](size_t i) { return p[i]; }
+  void resize(size_t m) {
+    if (m > cap) {
+      size_t c = cap ? cap * 2 : 1024;
+      if (c < m) c = m;
+      T *q = (T *)host_pool_alloc(c * sizeof(T));
+      if (n) memcpy(q, p, n * sizeof(T));
+      host_pool_free(p);
+      p = q;
+      cap = c;
+    }
+    n = m;
+  }
+  T *release() {  // never returns NULL so callers can always free()/index
+    if (!p) p = (T *)host_pool_alloc(sizeof(T));
+    T *q = p;
+    p = nullptr;
+    n = cap = 0;
+    return q;
+  }
+};
 struct HostEdges {
-  std::vector<uint64_t> rows, cols, dist, ncomp;
-  std::vector<double> p0_log, eK, datediff;  // filled when the fused transmission path ran on the device
+  HostCol<uint64_t> rows, cols, dist, ncomp;
+  HostCol<double> p0_log, eK, datediff;  // filled when the fused transmission path ran on the device
   bool has_trans = false;
 };
 const std::vector<double> &lgamma_table(size_t n);

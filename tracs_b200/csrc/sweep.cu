@@ -464,6 +464,28 @@ k_refine(const uint64_t *__restrict__ ckeys, const uint32_t *__restrict__ cdvals
   }
 }
 
+// Locality order for K2: rep[s] = smallest sample linked to s by an edge (the cluster's first member
+// for clique-like clusters). Edges are processed grouped by rep[row], so the N-plane rows of one
+// cluster stay in L2 while all of its edges are evaluated. Purely a schedule: results are written
+// to each edge's own slot.
+__global__ void k_rep_init(uint32_t *rep, uint32_t n) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) rep[s] = s;
+}
+__global__ void k_rep_min(const uint64_t *__restrict__ keys, uint64_t E, uint32_t *rep) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const uint64_t k = keys[e];
+  atomicMin(rep + (k & 0xFFFFFFFFull), (uint32_t)(k >> 32));
+}
+__global__ void k_rep_keys(const uint64_t *__restrict__ keys, uint64_t E, const uint32_t *__restrict__ rep,
+                           uint32_t *__restrict__ okey, uint32_t *__restrict__ oval) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  okey[e] = rep[keys[e] >> 32];
+  oval[e] = (uint32_t)e;
+}
+
 // ------------------------------------------------------------------------------------------
 // K2: compared sites. nn = L - |N_i u N_j| = L - (|N_i| + |N_j| - |N_i n N_j|).
 // The intersection walks the block summaries (1 bit / 128 sites) and touches the N-plane only
@@ -472,10 +494,11 @@ k_refine(const uint64_t *__restrict__ ckeys, const uint32_t *__restrict__ cdvals
 __global__ void __launch_bounds__(256)
 k_ncomp(const uint64_t *__restrict__ keys, uint64_t E, const uint32_t *__restrict__ nplane, uint64_t npitch,
         const uint8_t *__restrict__ nsum, uint64_t spitch, const uint32_t *__restrict__ ncount, uint64_t L,
-        uint64_t *__restrict__ ncomp) {
-  const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const uint32_t *__restrict__ order, uint64_t *__restrict__ ncomp) {
+  const uint64_t slot = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  if (e >= E) return;
+  if (slot >= E) return;
+  const uint64_t e = order ? order[slot] : slot;  // processing order groups edges of one cluster (L2 reuse)
   const uint64_t k = keys[e];
   const uint64_t i = k >> 32, j = k & 0xFFFFFFFFull;
   const uint32_t *si = reinterpret_cast<const uint32_t *>(nsum + i * spitch);
@@ -821,7 +844,23 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     if (want_n) {
       T.start();
       d_nc.alloc(E);
-      k_ncomp<<<(unsigned)((E * 32 + 255) / 256), 256, 0, st>>>(keys2.p, E, nplane.p, npitch, nsum.p, spitch, ncount.p, L, d_nc.p);
+      const uint32_t *order = nullptr;
+      DevBuf<uint32_t> rep, ok1, ok2, ov1, ov2;
+      DevBuf<uint8_t> otmp;
+      if (E >= 4096 && E < (1ull << 32)) {
+        rep.alloc(n); ok1.alloc(E); ok2.alloc(E); ov1.alloc(E); ov2.alloc(E);
+        k_rep_init<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rep.p, (uint32_t)n);
+        k_rep_min<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, E, rep.p);
+        k_rep_keys<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, E, rep.p, ok1.p, ov1.p);
+        size_t ob = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, ob, ok1.p, ok2.p, ov1.p, ov2.p, (int64_t)E, 0, end_bit - 32, st);
+        otmp.alloc(ob);
+        cub::DeviceRadixSort::SortPairs(otmp.p, ob, ok1.p, ok2.p, ov1.p, ov2.p, (int64_t)E, 0, end_bit - 32, st);
+        S.kernel_launches += 5 + (end_bit - 32 + 7) / 8;
+        order = ov2.p;
+      }
+      k_ncomp<<<(unsigned)((E * 32 + 255) / 256), 256, 0, st>>>(keys2.p, E, nplane.p, npitch, nsum.p, spitch, ncount.p, L, order,
+                                                              d_nc.p);
       S.kernel_launches++;
       TRACS_CK(cudaGetLastError());
       S.ms_ncomp += T.stop();
@@ -843,6 +882,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       S.ms_trans += T.stop();
     }
     const size_t old = out.rows.size();
+    T.start();
     if (fuse_trans) {
       out.p0_log.resize(old + E); out.eK.resize(old + E); out.datediff.resize(old + E);
       TRACS_CK(cudaMemcpyAsync(out.p0_log.data() + old, d_p0.p, E * 8, cudaMemcpyDeviceToHost, st));
@@ -850,12 +890,14 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       TRACS_CK(cudaMemcpyAsync(out.datediff.data() + old, d_dt.p, E * 8, cudaMemcpyDeviceToHost, st));
       S.d2h_bytes += E * 24;
     }
-    out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E); out.ncomp.resize(old + E, 0);
+    out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E);
+    if (want_n) out.ncomp.resize(old + E);
     TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaMemcpyAsync(out.dist.data() + old, d_dist.p, E * 8, cudaMemcpyDeviceToHost, st));
     if (want_n) TRACS_CK(cudaMemcpyAsync(out.ncomp.data() + old, d_nc.p, E * 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaStreamSynchronize(st));
+    S.ms_d2h += T.stop();
     S.d2h_bytes += E * 8 * (want_n ? 4 : 3);
     S.n_edges += E;
   }

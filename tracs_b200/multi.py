@@ -15,9 +15,10 @@ def merge_sorted(parts):
     return allp[:, order]
 
 
-def gather_edges(res, rank, world, dist, torch, device):
-    """All ranks call this; rank 0 gets the merged float64[6][E] table (rows, cols, d, ncomp, p0, eK),
-    the others get None. Integer columns stay exact in float64 (< 2^53)."""
+def gather_edges(res, rank, world, dist, torch, device, merge=True):
+    """All ranks call this; rank 0 gets the float64[6][E] table (rows, cols, d, ncomp, p0, eK) merged into
+    (row, col) order -- or, with merge=False, the list of per-rank tables (one MSA per rank) -- the
+    others get None. Integer columns stay exact in float64 (< 2^53)."""
     n_loc = len(res["rows"])
     cnt = torch.tensor([n_loc], dtype=torch.int64, device=device)
     cnts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
@@ -33,6 +34,7 @@ def gather_edges(res, rank, world, dist, torch, device):
     if rank == 0:
         bufs = [torch.empty_like(t) for _ in range(world)]
         dist.gather(t, bufs, dst=0)
-        return merge_sorted([b[:, :cnts[r]].cpu().numpy() for r, b in enumerate(bufs)])
+        parts = [b[:, :cnts[r]].cpu().numpy() for r, b in enumerate(bufs)]
+        return merge_sorted(parts) if merge else parts
     dist.gather(t, None, dst=0)
     return None
