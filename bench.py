@@ -108,7 +108,7 @@ def load_reference():
     return _Port, "port", "oracle/liboracle.so"
 
 
-def run_reference(args):
+def run_reference(args, saved_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -135,7 +135,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "site-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(saved_stdout, line)
     return 0
 
 
@@ -190,7 +190,22 @@ class Clocks:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL's version banner, for one) print to fd 1,
+    so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line):
+    sys.stdout.flush()
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    saved_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -204,13 +219,13 @@ def main():
     ap.add_argument("--shard", default="msa", choices=["msa", "tiles"], help="N>1: one MSA per GPU (weak) or row-blocks of one MSA (strong)")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, saved_stdout)
     args.warmup = max(args.warmup, 3)
 
     import torch
     import tracs_b200
     from tracs_b200 import _lib
-    from tracs_b200.multi import gather_edges
+    from tracs_b200.multi import EdgeGather
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -221,9 +236,13 @@ def main():
     _lib.check(_lib.lib().tracs_set_device(local))
     device = torch.device("cuda", local)
     dist_mod = None
+    gatherer = None
     if world > 1:
+        # keep NCCL's own banner / debug lines off stdout: the contract is ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
+        gatherer = EdgeGather(torch, dist_mod, device, rank, world)
 
     w = dict(WORKLOAD)
     if args.n:
@@ -251,7 +270,7 @@ def main():
     def step():
         res = tracs_b200.pairsnp_device(seqs.data_ptr(), n, L, pitch, copy=False, **kw)
         st = tracs_b200.last_stats()
-        merged = gather_edges(res, rank, world, dist_mod, torch, device, merge=by_tiles) if world > 1 else res
+        merged = gatherer.gather(res, merge=by_tiles) if world > 1 else res
         return res, st, merged
 
     def sync():
@@ -294,10 +313,8 @@ def main():
         st = stats[-1]
         if isinstance(merged, dict):
             n_edges = len(merged["rows"])
-        elif isinstance(merged, list):
-            n_edges = int(sum(p.shape[1] for p in merged))
         else:
-            n_edges = merged.shape[1]
+            n_edges = int(sum(len(p["rows"]) for p in merged))
         launches = int(sum(s["kernel_launches"] for s in stats))
         # ---- rooflines ---------------------------------------------------------------------------
         # k_sweep (INT-pipe bound): algorithmic work = 6 INT instructions per 32-site word-pair
@@ -429,7 +446,7 @@ def main():
         line["cpu_baseline"] = {"value": None, "note": "timed at N=1 only"}
 
     if rank == 0:
-        print(json.dumps(line))
+        _emit(saved_stdout, line)
     if world > 1:
         dist_mod.barrier()
         dist_mod.destroy_process_group()

@@ -67,6 +67,7 @@ typedef struct tracs_stats {
   float ms_trans;            /* transmission LUT + gather (K3)                              */
   float ms_total;            /* device time of the whole call (events on the call's stream) */
   float ms_d2h;              /* edge columns device -> host                                  */
+  float ms_filter;           /* recombination filter (K4), only when filter != 0             */
 } tracs_stats_t;
 
 /* Options shared by the matrix-input entry points. Zero-initialise, then set. */

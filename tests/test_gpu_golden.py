@@ -80,3 +80,15 @@ def test_reference_kat_csv(tmp_path):
     assert abs(float(l1[4]) - 0.23794988406662973) < 1e-6 and abs(float(l2[4]) - 0.024467137572328577) < 1e-6
     assert abs(float(l1[5]) - 2.6335200453700187) < 1e-6 and abs(float(l2[5]) - 7.315670110063259) < 1e-6
     assert rows[3][:4] == ["seq2", "seq3", "0.0", "1"] and rows[3][6:] == ["NA", "9", "kat"]
+
+
+def test_distance_cli_with_filter(tmp_path, ):
+    # --filter: filtered column carries numbers, likelihood uses them; compare with the CPU oracle pipeline
+    from oracle import oracle
+    from tracs_b200 import distance
+    out = str(tmp_path / "f.csv")
+    msa = os.path.join(GOLD, "cli_combined.fasta.gz")
+    distance.distance([msa], out, snp_threshold=40, recomb_filter=True, metadata=os.path.join(GOLD, "cli_dates.csv"), trans_threshold=1e9)
+    rows = _rows(out)[1:]
+    exp = oracle.pairsnp([msa], dist=40, filter=True)
+    assert [int(r[6]) for r in rows] == exp[4] and [int(r[3]) for r in rows] == exp[2]

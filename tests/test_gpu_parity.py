@@ -154,3 +154,39 @@ def test_min_over_refs():
     ks = sorted(exp)
     assert list(zip(oa.tolist(), ob.tolist())) == ks
     assert ov.tolist() == [exp[k] for k in ks]
+
+
+def test_recombination_filter(oracle_mod):
+    # filter=True (src/pairsnp.hpp:251-318): scattered SNPs plus a dense block that must be removed
+    s = synth.generate(24, 60_000, p_var=0.02, n_clusters=3, mu=6, p_N=0.002, p_amb=0.01, seed=51)
+    rng = np.random.default_rng(2)
+    for k in range(0, 24, 3):                      # recombination-like blocks: 30 substitutions inside 400 bp
+        start = int(rng.integers(1000, 59000))
+        sites = start + rng.choice(400, size=30, replace=False)
+        s[k, sites] = np.where(s[k, sites] == ord("A"), ord("C"), ord("A"))
+    for dist in (IMAX, 150):
+        res = tracs_b200.pairsnp_matrix(s, dist=dist, filter=True)
+        r, c, d, f, nn = oracle_mod.pairsnp_ascii(s, dist=dist, filter=True, n_threads=4)
+        assert res["rows"].tolist() == r.tolist() and res["dist"].tolist() == d.tolist()
+        assert res["filt"].tolist() == f.tolist()
+        assert (f < d).any() and res["ncomp"].tolist() == nn.tolist()
+
+
+def test_filter_golden_and_fused_trans(oracle_mod):
+    import json
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    G = json.load(open(os.path.join(gold, "golden.json")))
+    for case in G["filter"]:
+        r = tracs_b200.pairsnp(fasta=[os.path.join(gold, case["fasta"])], n_threads=1, dist=case["dist"], filter=True)
+        assert r[0] == case["rows"] and r[2] == case["d"] and r[4] == case["filt"]
+    # fused likelihood is fed the FILTERED distance when the filter is on (tracs/distance.py:182-192)
+    s = synth.generate(60, 30_000, p_var=0.03, n_clusters=4, mu=5, p_N=0.002, seed=52)
+    days = np.random.default_rng(3).integers(0, 100, size=60).astype(np.int32)
+    res = tracs_b200.pairsnp_matrix(s, dist=200, filter=True, days=days)
+    r, c, d, f, nn = oracle_mod.pairsnp_ascii(s, dist=200, filter=True)
+    assert res["filt"].tolist() == f.tolist()
+    dt = np.abs(days[r.astype(int)] * 86400.0 - days[c.astype(int)] * 86400.0) / 31556952.0
+    op0, oeK = oracle_mod.trans_dist(f.astype(np.int32), dt, 29.903, 73.0, 0.01)
+    assert np.allclose(res["p0_log"], op0, rtol=1e-6, atol=0)
+    pos = dt > 0
+    assert np.allclose(res["eK"][pos], oeK[pos], rtol=1e-6, atol=0)

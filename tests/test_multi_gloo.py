@@ -28,10 +28,15 @@ def _worker(rank, world, port, q):
     merged = gather_edges(res, rank, world, dist, torch, torch.device("cpu"))
     ok = True
     if rank == 0:
-        ok = (merged[0].astype(np.uint64).tolist() == r.tolist() and merged[1].astype(np.uint64).tolist() == c.tolist()
-              and merged[2].astype(np.uint64).tolist() == d.tolist() and merged[3].astype(np.uint64).tolist() == nn.tolist())
+        ok = (merged["rows"].tolist() == r.tolist() and merged["cols"].tolist() == c.tolist()
+              and merged["dist"].tolist() == d.tolist() and merged["ncomp"].tolist() == nn.tolist())
+        parts = None
     else:
         ok = merged is None
+    # one-MSA-per-rank mode: per-rank tables come back unmerged, in rank order
+    parts = gather_edges(res, rank, world, dist, torch, torch.device("cpu"), merge=False)
+    if rank == 0:
+        ok = ok and len(parts) == world and parts[0]["rows"].tolist() == r[keep].tolist() and sum(len(p["rows"]) for p in parts) == len(r)
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, bool(ok), int(keep.sum())))

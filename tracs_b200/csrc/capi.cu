@@ -139,8 +139,7 @@ static void finish_edges(HostEdges &he, const tracs_opts_t &o, uint64_t n, uint6
                          cudaStream_t st) {
   const size_t E = he.rows.size();
   out->n_edges = E;
-  out->filt = (uint64_t *)host_pool_alloc(std::max<size_t>(1, E) * sizeof(uint64_t));
-  memset(out->filt, 0, std::max<size_t>(1, E) * sizeof(uint64_t));
+  const bool have_filt = o.filter && he.filt.size() == E;
   out->seq_length = L;
   if (he.ncomp.size() != E) {  // compared sites not requested: zeros
     he.ncomp.resize(E);
@@ -158,12 +157,18 @@ static void finish_edges(HostEdges &he, const tracs_opts_t &o, uint64_t n, uint6
     for (size_t e = 0; e < E; ++e) {
       const double ti = (double)o.days[he.rows[e]] * 86400.0, tj = (double)o.days[he.cols[e]] * 86400.0;
       dt[e] = fabs(ti - tj) / 31556952.0;
-      d32[e] = (int32_t)he.dist[e];
+      d32[e] = (int32_t)(have_filt ? he.filt[e] : he.dist[e]);
     }
     trans_dist_device(d32.data(), dt.data(), E, o.lamb, o.beta, o.threshold_Ek, p0.data(), ek.data(), st);
     out->p0_log = dup_array(p0);
     out->eK = dup_array(ek);
     out->datediff = dup_array(dt);
+  }
+  if (have_filt) {
+    out->filt = he.filt.release();
+  } else {  // filter off: zeros, like the reference's filt_distances (src/pairsnp.hpp:452)
+    out->filt = (uint64_t *)host_pool_alloc(std::max<size_t>(1, E) * sizeof(uint64_t));
+    memset(out->filt, 0, std::max<size_t>(1, E) * sizeof(uint64_t));
   }
   out->rows = he.rows.release();
   out->cols = he.cols.release();
@@ -342,7 +347,6 @@ int tracs_pairsnp_device(const uint8_t *dev_seqs, size_t n, size_t L, size_t pit
   return guarded([&] {
     require_device();
     tracs_opts_t o = normalise(opts, n);
-    if (o.filter) throw std::runtime_error("tracs_b200: filter=True (recombination filter) is not implemented yet");
     HostEdges he;
     sweep_device(dev_seqs, n, L, pitch, o, he, 0);
     finish_edges(he, o, n, L, out, 0);
@@ -356,7 +360,6 @@ int tracs_pairsnp_host(const uint8_t *seqs, size_t n, size_t L, size_t pitch, co
   return guarded([&] {
     require_device();
     tracs_opts_t o = normalise(opts, n);
-    if (o.filter) throw std::runtime_error("tracs_b200: filter=True (recombination filter) is not implemented yet");
     HostEdges he;
     if (n > 0) {
       const size_t dp = std::max<size_t>(32, (L + 31) / 32 * 32);

@@ -145,7 +145,7 @@ struct HostCol {
   }
 };
 struct HostEdges {
-  HostCol<uint64_t> rows, cols, dist, ncomp;
+  HostCol<uint64_t> rows, cols, dist, ncomp, filt;
   HostCol<double> p0_log, eK, datediff;  // filled when the fused transmission path ran on the device
   bool has_trans = false;
 };

@@ -464,6 +464,110 @@ k_refine(const uint64_t *__restrict__ ckeys, const uint32_t *__restrict__ cdvals
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K4: recombination filter for emitted edges (filter=True). Restates src/pairsnp.hpp:251-318:
+//   p = d / L; half-window h = clamp(int(1/p/2 + 1), 50, 5000); for every SNP of the pair, count the
+//   pair's SNPs inside [pos-h, pos+h+1) (clipped to the alignment) and their span last-first+1
+//   (range_count :223-248); the SNP is kept if it is alone in its window or
+//   1 - BinomCDF(count; span, p) >= 0.05 / d.  filt = number of SNPs kept; d <= 1 -> d.
+// SNPs only occur at variable sites, so positions come from the compacted planes + site index.
+// The binomial CDF is summed term by term in fp64 (Boost uses the incomplete beta function: same
+// value to rounding; see DESIGN.md "unpinned corner").
+// Pass 1 (one warp per edge): ordered SNP positions into a scratch list. Pass 2: the window test.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_snp_positions(const uint64_t *__restrict__ keys, uint64_t e0, uint64_t e1, const uint4 *__restrict__ planesT, uint32_t Wp,
+                const uint32_t *__restrict__ site_idx, uint64_t V, const uint64_t *__restrict__ offs, uint64_t base,
+                uint32_t *__restrict__ pos) {
+  const uint64_t e = e0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  if (e >= e1) return;
+  const uint64_t k = keys[e];
+  const uint4 *ri = planesT + (k >> 32) * Wp;
+  const uint4 *rj = planesT + (k & 0xFFFFFFFFull) * Wp;
+  uint32_t *out = pos + (offs[e] - base);
+  uint32_t written = 0;
+  for (uint32_t w0 = 0; w0 < Wp; w0 += 32) {
+    const uint32_t w = w0 + lane;
+    uint32_t mis = 0;
+    if (w < Wp) {
+      const uint4 x = __ldg(ri + w), y = __ldg(rj + w);
+      mis = ~((x.x & y.x) | (x.y & y.y) | (x.z & y.z) | (x.w & y.w));
+    }
+    const uint32_t c = __popc(mis);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    uint32_t at = written + incl - c;
+    while (mis) {
+      const uint32_t b = __ffs(mis) - 1;
+      mis &= mis - 1;
+      const uint64_t v = (uint64_t)w * 32 + b;
+      out[at++] = v < V ? site_idx[v] : 0u;  // v >= V cannot happen: pad bits always match
+    }
+    written += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_filter_recomb(const uint32_t *__restrict__ dvals, uint64_t e0, uint64_t e1, const uint64_t *__restrict__ offs, uint64_t base,
+                const uint32_t *__restrict__ pos, uint64_t L, const double *__restrict__ lg, uint32_t *__restrict__ filt) {
+  const uint64_t e = e0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  if (e >= e1) return;
+  const uint32_t d = dvals[e];
+  if (d <= 1) {
+    if (lane == 0) filt[e] = d;
+    return;
+  }
+  const uint32_t *ps = pos + (offs[e] - base);
+  const int aln = (int)L;
+  const double dd = (double)d;
+  const double p = dd / aln, thr = 0.05 / dd;
+  int h = (int)(1.0 / p / 2.0 + 1);
+  h = min(h, 5000);
+  h = max(h, 50);
+  const double lp = log(p), lq = log1p(-p);
+  uint32_t kept = 0;
+  for (uint32_t s = lane; s < d; s += 32) {
+    const int i = (int)ps[s];
+    const int left = max(0, i - h), right = min(aln, i + h + 1);
+    // first SNP >= left, first SNP >= right
+    uint32_t lo = 0, hi = s;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if ((int)ps[m] < left) lo = m + 1; else hi = m; }
+    const uint32_t a = lo;
+    lo = s; hi = d;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if ((int)ps[m] < right) lo = m + 1; else hi = m; }
+    const uint32_t b = lo;
+    const uint32_t cnt = b - a;
+    if (cnt > 1) {
+      const double n = (double)(int)(ps[b - 1] - ps[a] + 1), kk = (double)(int)cnt;
+      double cdf;
+      if (kk >= n) cdf = 1.0;
+      else {
+        cdf = 0.0;
+        const int ni = (int)n;
+        for (int t = 0; t <= (int)cnt; ++t)
+          cdf += exp(lg[ni + 1] - lg[t + 1] - lg[ni - t + 1] + (double)t * lp + (double)(ni - t) * lq);
+        if (cdf > 1.0) cdf = 1.0;
+      }
+      if (1.0 - cdf >= thr) kept++;
+    } else {
+      kept++;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
+  if (lane == 0) filt[e] = kept;
+}
+__global__ void k_widen(const uint32_t *__restrict__ in, uint64_t E, uint64_t *__restrict__ out) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) out[e] = in[e];
+}
+
 // Locality order for K2: rep[s] = smallest sample linked to s by an edge (the cluster's first member
 // for clique-like clusters). Edges are processed grouped by rep[row], so the N-plane rows of one
 // cluster stay in L2 while all of its edges are evaluated. Purely a schedule: results are written
@@ -650,7 +754,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     TRACS_CK(cudaGetLastError());
   }
   S.ms_compact = T.stop();
-  site_idx.release();
+  if (!o.filter) site_idx.release();
 
   // ---- tile lists ------------------------------------------------------------------------
   const uint32_t n_rb_all = (uint32_t)((i_end + TILE - 1) / TILE);
@@ -841,6 +945,65 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     S.kernel_launches++;
     S.ms_sort += T.stop();
 
+    DevBuf<uint32_t> d_filt32;
+    DevBuf<uint64_t> d_filt64;
+    if (o.filter) {
+      T.start();
+      d_filt32.alloc(E);
+      d_filt64.alloc(E);
+      DevBuf<uint64_t> offs(E + 1);
+      DevBuf<uint8_t> stmp;
+      size_t sb = 0;
+      TRACS_CK(cudaMemsetAsync(offs.p, 0, sizeof(uint64_t), st));
+      cub::DeviceScan::InclusiveSum(nullptr, sb, dv2.p, offs.p + 1, (int64_t)E, st);
+      stmp.alloc(sb);
+      cub::DeviceScan::InclusiveSum(stmp.p, sb, dv2.p, offs.p + 1, (int64_t)E, st);
+      uint64_t total = 0;
+      TRACS_CK(cudaMemcpyAsync(&total, offs.p + E, 8, cudaMemcpyDeviceToHost, st));
+      TRACS_CK(cudaStreamSynchronize(st));
+      const uint64_t LIMIT = 1ull << 29;  // SNP positions held at once (2 GB)
+      std::vector<uint64_t> cuts{0};
+      if (total > LIMIT) {
+        std::vector<uint64_t> h(E + 1);
+        TRACS_CK(cudaMemcpyAsync(h.data(), offs.p, (E + 1) * 8, cudaMemcpyDeviceToHost, st));
+        TRACS_CK(cudaStreamSynchronize(st));
+        uint64_t start = 0;
+        for (uint64_t e = 0; e < E; ++e) {
+          if (h[e + 1] - h[start] > LIMIT && e > start) {
+            cuts.push_back(e);
+            start = e;
+          }
+          if (h[e + 1] - h[e] > LIMIT) throw std::runtime_error("filter: a single pair has too many SNPs for the position scratch");
+        }
+        cuts.push_back(E);
+        // per-cut sizes
+        uint64_t mxn = 0;
+        for (size_t c = 0; c + 1 < cuts.size(); ++c) mxn = std::max(mxn, h[cuts[c + 1]] - h[cuts[c]]);
+        total = mxn;
+      } else {
+        cuts.push_back(E);
+      }
+      DevBuf<uint32_t> pos(std::max<uint64_t>(1, total));
+      const size_t nlg = 10000 + 16;
+      const std::vector<double> &lgh = lgamma_table(nlg);
+      DevBuf<double> lg_f(nlg);
+      TRACS_CK(cudaMemcpyAsync(lg_f.p, lgh.data(), nlg * 8, cudaMemcpyHostToDevice, st));
+      for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        const uint64_t e0 = cuts[c], e1 = cuts[c + 1];
+        if (e1 == e0) continue;
+        uint64_t base = 0;
+        TRACS_CK(cudaMemcpyAsync(&base, offs.p + e0, 8, cudaMemcpyDeviceToHost, st));
+        TRACS_CK(cudaStreamSynchronize(st));
+        const unsigned g = (unsigned)(((e1 - e0) * 32 + 255) / 256);
+        k_snp_positions<<<g, 256, 0, st>>>(keys2.p, e0, e1, planesT.p, Wp, site_idx.p, V, offs.p, base, pos.p);
+        k_filter_recomb<<<g, 256, 0, st>>>(dv2.p, e0, e1, offs.p, base, pos.p, L, lg_f.p, d_filt32.p);
+        S.kernel_launches += 2;
+        TRACS_CK(cudaGetLastError());
+      }
+      k_widen<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(d_filt32.p, E, d_filt64.p);
+      S.kernel_launches += 3;
+      S.ms_filter += T.stop();
+    }
     if (want_n) {
       T.start();
       d_nc.alloc(E);
@@ -870,12 +1033,14 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       T.start();
       d_p0.alloc(E); d_eK.alloc(E); d_dt.alloc(E);
       TRACS_CK(cudaMemsetAsync(used.p, 0, lut_size, st));
-      k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dv2.p, E, d_days.p, DD, used.p);
+      // with the filter on, the likelihood is fed the filtered distance (tracs/distance.py:182-192)
+      const uint32_t *dtrans = o.filter ? d_filt32.p : dv2.p;
+      k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dtrans, E, d_days.p, DD, used.p);
       cub::CountingInputIterator<uint32_t> cnt_it(0);
       cub::DeviceSelect::Flagged(sel_tmp.p, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
       k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, st>>>(key_idx.p, n_keys.p, DD, d_lg.p, o.lamb, o.beta, o.threshold_Ek,
                                                                     p0_lut.p, eK_lut.p);
-      k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dv2.p, E, d_days.p, DD, p0_lut.p, eK_lut.p, d_p0.p,
+      k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dtrans, E, d_days.p, DD, p0_lut.p, eK_lut.p, d_p0.p,
                                                                  d_eK.p, d_dt.p);
       S.kernel_launches += 5;
       TRACS_CK(cudaGetLastError());
@@ -892,6 +1057,10 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     }
     out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E);
     if (want_n) out.ncomp.resize(old + E);
+    if (o.filter) {
+      out.filt.resize(old + E);
+      TRACS_CK(cudaMemcpyAsync(out.filt.data() + old, d_filt64.p, E * 8, cudaMemcpyDeviceToHost, st));
+    }
     TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaMemcpyAsync(out.dist.data() + old, d_dist.p, E * 8, cudaMemcpyDeviceToHost, st));

@@ -1,40 +1,106 @@
-"""Multi-GPU plumbing for the pair sweep: one process per GPU, each sweeps the row-blocks dealt to its
-rank (tracs_opts_t.shard_rank/shard_world; no traffic during the sweep), then ONE variable-length
-gather of the edge columns to rank 0, merged back into (row, col) order. torch.distributed is the
-transport (NCCL on GPUs; gloo in the CPU tests)."""
+"""Multi-GPU plumbing for the pair sweep: one process per GPU.
+
+Two ways to shard (both without any traffic during the sweep):
+  * one MSA per rank -- the loop `for msa in args.msa_files` of tracs/distance.py:159 (weak scaling);
+  * row-blocks of ONE alignment dealt to ranks (tracs_opts_t.shard_rank/shard_world, strong scaling).
+Either way the only exchange is ONE variable-length gather of the edge columns to rank 0.
+torch.distributed is the transport (NCCL on GPUs; gloo in the CPU tests). Columns travel in a
+compact 32 B/edge layout (u32 row, col, d, compared sites; f64 log p0, E[K]) through a cached
+page-locked staging buffer."""
 import numpy as np
 
 COLUMNS = ("rows", "cols", "dist", "ncomp", "p0_log", "eK")
+_DTYPES = (np.uint32, np.uint32, np.uint32, np.uint32, np.float64, np.float64)
+_BYTES_PER_EDGE = 4 * 4 + 2 * 8
+TILE = 128
 
 
-def merge_sorted(parts):
-    """parts: list of float64[6][E_r] blocks, each sorted by (row, col) and with disjoint rows."""
-    allp = np.concatenate(parts, axis=1) if parts else np.zeros((len(COLUMNS), 0))
-    key = (allp[0].astype(np.uint64) << np.uint64(32)) | allp[1].astype(np.uint64)
-    order = np.argsort(key, kind="stable")
-    return allp[:, order]
+def shard_owner(row_block, world):
+    """Same deal as the library's shard_owner() (csrc/common.cuh): boustrophedon over ranks."""
+    rnd, pos = divmod(row_block, world)
+    return (world - 1 - pos) if (rnd & 1) else pos
+
+
+def _sections(buf, mx):
+    """Typed views of the six column sections inside a flat uint8 numpy buffer of 32*mx bytes."""
+    out, off = [], 0
+    for dt in _DTYPES:
+        nb = np.dtype(dt).itemsize * mx
+        out.append(buf[off:off + nb].view(dt))
+        off += nb
+    return out
+
+
+def merge_by_rowblock(parts, world):
+    """parts[r]: dict of columns from rank r, each sorted by (row, col); row-blocks were dealt by
+    shard_owner. Returns the columns concatenated in global (row, col) order without sorting."""
+    top = 0
+    for p in parts:
+        if len(p["rows"]):
+            top = max(top, int(p["rows"][-1]))
+    n_rb = top // TILE + 1
+    bounds = [np.searchsorted(p["rows"], np.arange(n_rb + 1, dtype=np.uint64) * TILE) for p in parts]
+    out = {}
+    for c in COLUMNS:
+        out[c] = np.concatenate([parts[shard_owner(rb, world)][c][bounds[shard_owner(rb, world)][rb]:bounds[shard_owner(rb, world)][rb + 1]]
+                                 for rb in range(n_rb)]) if n_rb else parts[0][c][:0]
+    return out
+
+
+class EdgeGather:
+    """Reusable gather: keeps its pinned / device staging buffers between steps."""
+
+    def __init__(self, torch, dist, device, rank, world):
+        self.torch, self.dist, self.device, self.rank, self.world = torch, dist, device, rank, world
+        self.pinned = device.type == "cuda"
+        self.send = None
+        self.recv = None
+
+    def _host(self, nbytes, old):
+        if old is not None and old.numel() >= nbytes:
+            return old
+        return self.torch.empty(int(nbytes * 1.25) + 64, dtype=self.torch.uint8, pin_memory=self.pinned)
+
+    def gather(self, res, merge=True):
+        """All ranks call this. Rank 0 returns the merged dict of columns (merge=True: row-block
+        shards of one alignment) or the list of per-rank dicts (merge=False: one MSA per rank);
+        other ranks return None."""
+        torch, dist = self.torch, self.dist
+        n_loc = len(res["rows"])
+        cnt = torch.tensor([n_loc], dtype=torch.int64, device=self.device)
+        cnts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
+        dist.all_gather(cnts, cnt)
+        cnts = [int(c.item()) for c in cnts]
+        mx = max(cnts + [1])
+        nbytes = _BYTES_PER_EDGE * mx
+        self.send = self._host(nbytes, self.send)
+        secs = _sections(self.send.numpy()[:nbytes], mx)
+        for sec, c in zip(secs, COLUMNS):
+            v = res.get(c)
+            if v is not None and n_loc:
+                sec[:n_loc] = v
+            elif n_loc:
+                sec[:n_loc] = 0
+        dsend = self.send[:nbytes].to(self.device, non_blocking=True)
+        if self.rank != 0:
+            dist.gather(dsend, None, dst=0)
+            return None
+        bufs = [torch.empty_like(dsend) for _ in range(self.world)]
+        dist.gather(dsend, bufs, dst=0)
+        self.recv = self._host(nbytes * self.world, self.recv)
+        flat = self.recv[:nbytes * self.world]
+        for r, b in enumerate(bufs):
+            flat[r * nbytes:(r + 1) * nbytes].copy_(b, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        host = flat.numpy()
+        parts = []
+        for r in range(self.world):
+            secs = _sections(host[r * nbytes:(r + 1) * nbytes], mx)
+            parts.append({c: s[:cnts[r]] for c, s in zip(COLUMNS, secs)})
+        return merge_by_rowblock(parts, self.world) if merge else parts
 
 
 def gather_edges(res, rank, world, dist, torch, device, merge=True):
-    """All ranks call this; rank 0 gets the float64[6][E] table (rows, cols, d, ncomp, p0, eK) merged into
-    (row, col) order -- or, with merge=False, the list of per-rank tables (one MSA per rank) -- the
-    others get None. Integer columns stay exact in float64 (< 2^53)."""
-    n_loc = len(res["rows"])
-    cnt = torch.tensor([n_loc], dtype=torch.int64, device=device)
-    cnts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(cnts, cnt)
-    cnts = [int(c.item()) for c in cnts]
-    mx = max(cnts + [1])
-    pack = np.zeros((len(COLUMNS), mx), dtype=np.float64)
-    for k, c in enumerate(COLUMNS):
-        v = res.get(c)
-        if v is not None and n_loc:
-            pack[k, :n_loc] = v
-    t = torch.from_numpy(pack).to(device)
-    if rank == 0:
-        bufs = [torch.empty_like(t) for _ in range(world)]
-        dist.gather(t, bufs, dst=0)
-        parts = [b[:, :cnts[r]].cpu().numpy() for r, b in enumerate(bufs)]
-        return merge_sorted(parts) if merge else parts
-    dist.gather(t, None, dst=0)
-    return None
+    """One-shot convenience wrapper around EdgeGather."""
+    return EdgeGather(torch, dist, device, rank, world).gather(res, merge=merge)
