@@ -225,7 +225,7 @@ def main():
     import torch
     import tracs_b200
     from tracs_b200 import _lib
-    from tracs_b200.multi import EdgeGather
+    from tracs_b200.multi import PipelinedGather
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -242,7 +242,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
-        gatherer = EdgeGather(torch, dist_mod, device, rank, world)
+        gatherer = None  # created once by_tiles is known
 
     w = dict(WORKLOAD)
     if args.n:
@@ -267,11 +267,17 @@ def main():
 
     peak = tracs_b200.int_peak() if rank == 0 else None
 
+    if world > 1:
+        gatherer = PipelinedGather(torch, dist_mod, device, rank, world, merge=by_tiles)
+
     def step():
+        """One pass of the hot path. At N > 1 the edge-list gather of this step is queued and overlaps
+        the next step's sweep; drain() below completes every gather inside the timed region."""
         res = tracs_b200.pairsnp_device(seqs.data_ptr(), n, L, pitch, copy=False, **kw)
         st = tracs_b200.last_stats()
-        merged = gatherer.gather(res, merge=by_tiles) if world > 1 else res
-        return res, st, merged
+        if world > 1:
+            gatherer.submit(res)
+        return res, st, res
 
     def sync():
         torch.cuda.synchronize()
@@ -281,6 +287,8 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    if world > 1:
+        gatherer.drain()
     sync()
     clocks = Clocks(local)
     if rank == 0:
@@ -292,6 +300,9 @@ def main():
     for _ in range(args.steps):
         res, st, merged = step()
         stats.append(st)
+    if world > 1:
+        gathered = gatherer.drain()   # every step's gather has landed on rank 0 before the clock stops
+        merged = gathered[-1] if rank == 0 else None
     ev1.record()
     sync()
     t_wall = time.perf_counter() - t_wall0
@@ -448,6 +459,7 @@ def main():
     if rank == 0:
         _emit(saved_stdout, line)
     if world > 1:
+        gatherer.close()
         dist_mod.barrier()
         dist_mod.destroy_process_group()
     return 0

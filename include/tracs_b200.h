@@ -44,6 +44,11 @@ typedef struct tracs_edges {
   size_t n_names;
   char **names;      /* n_names NUL-terminated strings, or NULL           */
   uint64_t seq_length;
+  /* tracs_opts_t.keep_on_device: the same columns, still in DEVICE memory, packed column-wise as
+   * u32 rows[n] | u32 cols[n] | u32 dist (filt if filter) [n] | u32 ncomp[n] | f64 p0_log[n] | f64 eK[n]
+   * (32 bytes per edge) so a multi-GPU caller can gather edge lists GPU-to-GPU. NULL otherwise. */
+  void *dev_packed;
+  size_t dev_packed_bytes;
 } tracs_edges_t;
 
 /* Per-call statistics of the last sweep on this thread (for bench.py / roofline accounting). */
@@ -83,7 +88,7 @@ typedef struct tracs_opts {
   const int32_t *days; /* host: sampling day number per sample (days since any epoch)            */
   double lamb, beta, threshold_Ek; /* trans_dist args (src/transcluster.hpp:241)                 */
   int32_t sweep_variant; /* 0 = prefilter + refine when the threshold allows; 1 = always full tile sweep */
-  int32_t keep_on_device; /* reserved */
+  int32_t keep_on_device; /* also return the edge columns packed in device memory (tracs_edges_t.dev_packed) */
 } tracs_opts_t;
 
 /* Replaces TRACS.pairsnp(fasta, n_threads, dist, filter) -- src/python_bindings.cpp:12-13,

@@ -190,3 +190,19 @@ def test_filter_golden_and_fused_trans(oracle_mod):
     assert np.allclose(res["p0_log"], op0, rtol=1e-6, atol=0)
     pos = dt > 0
     assert np.allclose(res["eK"][pos], oeK[pos], rtol=1e-6, atol=0)
+
+
+def test_device_packed_columns_match_host():
+    import torch
+    from tracs_b200.multi import _DevBytes, _sections, COLUMNS
+    s = synth.generate(300, 4000, p_var=0.05, n_clusters=4, mu=3, p_N=0.01, seed=61)
+    days = np.random.default_rng(1).integers(0, 50, size=300).astype(np.int32)
+    res = tracs_b200.pairsnp_matrix(s, dist=60, days=days, copy=False, keep_on_device=True)
+    ptr, nbytes = res["dev_packed"]
+    E = len(res["rows"])
+    assert nbytes == 32 * E and E > 0
+    host = torch.as_tensor(_DevBytes(ptr, nbytes), device="cuda").cpu().numpy()
+    secs = dict(zip(COLUMNS, _sections(host, E)))
+    for c in ("rows", "cols", "dist", "ncomp"):
+        assert secs[c].astype(np.uint64).tolist() == res[c].tolist()
+    assert np.array_equal(secs["p0_log"], res["p0_log"]) and np.array_equal(secs["eK"], res["eK"])

@@ -17,7 +17,8 @@ class Edges(C.Structure):
     _fields_ = [("n_edges", C.c_size_t), ("rows", C.POINTER(C.c_uint64)), ("cols", C.POINTER(C.c_uint64)),
                 ("dist", C.POINTER(C.c_uint64)), ("filt", C.POINTER(C.c_uint64)), ("ncomp", C.POINTER(C.c_uint64)),
                 ("p0_log", C.POINTER(C.c_double)), ("eK", C.POINTER(C.c_double)), ("datediff", C.POINTER(C.c_double)),
-                ("n_names", C.c_size_t), ("names", C.POINTER(C.c_char_p)), ("seq_length", C.c_uint64)]
+                ("n_names", C.c_size_t), ("names", C.POINTER(C.c_char_p)), ("seq_length", C.c_uint64),
+                ("dev_packed", C.c_void_p), ("dev_packed_bytes", C.c_size_t)]
 
 
 class Stats(C.Structure):
@@ -140,7 +141,8 @@ def take_edges(e, as_lists=False, names=True, copy=True):
     out = EdgeTable({"rows": arr(e.rows, np.uint64), "cols": arr(e.cols, np.uint64), "dist": arr(e.dist, np.uint64),
                      "filt": arr(e.filt, np.uint64), "ncomp": arr(e.ncomp, np.uint64), "p0_log": arr(e.p0_log, np.float64),
                      "eK": arr(e.eK, np.float64), "datediff": arr(e.datediff, np.float64), "seq_length": int(e.seq_length),
-                     "names": [e.names[i].decode() for i in range(e.n_names)] if (names and e.names) else []})
+                     "names": [e.names[i].decode() for i in range(e.n_names)] if (names and e.names) else [],
+                     "dev_packed": (int(e.dev_packed), int(e.dev_packed_bytes)) if (e.dev_packed and not copy) else None})
     if copy:
         lib().tracs_edges_free(C.byref(e))
     else:

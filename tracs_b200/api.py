@@ -64,7 +64,7 @@ def calculate_posteriors(counts, alphas, keep, threshold):
 # ---- extras (not in the reference module) ------------------------------------------------------
 
 def make_opts(dist=INT32_MAX, i_end=0, j_start=0, shard_rank=0, shard_world=1, want_ncomp=True, days=None, lamb=29.903,
-              beta=73.0, threshold_Ek=0.01, filter=False, full_sweep=False):
+              beta=73.0, threshold_Ek=0.01, filter=False, full_sweep=False, keep_on_device=False):
     o = Opts()
     o.dist = int(dist)
     o.filter = int(bool(filter))
@@ -74,6 +74,7 @@ def make_opts(dist=INT32_MAX, i_end=0, j_start=0, shard_rank=0, shard_world=1, w
     o.shard_world = int(shard_world)
     o.want_ncomp = int(bool(want_ncomp))
     o.sweep_variant = 1 if full_sweep else 0
+    o.keep_on_device = int(bool(keep_on_device))
     keep = None
     if days is not None:
         keep = np.ascontiguousarray(days, dtype=np.int32)

@@ -170,6 +170,9 @@ static void finish_edges(HostEdges &he, const tracs_opts_t &o, uint64_t n, uint6
     out->filt = (uint64_t *)host_pool_alloc(std::max<size_t>(1, E) * sizeof(uint64_t));
     memset(out->filt, 0, std::max<size_t>(1, E) * sizeof(uint64_t));
   }
+  out->dev_packed = he.dev_packed;
+  out->dev_packed_bytes = he.dev_packed_bytes;
+  he.dev_packed = nullptr;
   out->rows = he.rows.release();
   out->cols = he.cols.release();
   out->dist = he.dist.release();
@@ -325,6 +328,7 @@ void tracs_edges_free(tracs_edges_t *e) {
   if (!e) return;
   host_pool_free(e->rows); host_pool_free(e->cols); host_pool_free(e->dist); host_pool_free(e->filt); host_pool_free(e->ncomp);
   host_pool_free(e->p0_log); host_pool_free(e->eK); host_pool_free(e->datediff);
+  if (e->dev_packed) cudaFree(e->dev_packed);
   if (e->names) {
     for (size_t i = 0; i < e->n_names; ++i) free(e->names[i]);
     free(e->names);

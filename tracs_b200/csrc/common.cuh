@@ -148,6 +148,9 @@ struct HostEdges {
   HostCol<uint64_t> rows, cols, dist, ncomp, filt;
   HostCol<double> p0_log, eK, datediff;  // filled when the fused transmission path ran on the device
   bool has_trans = false;
+  void *dev_packed = nullptr;  // cudaMalloc'ed, see tracs_edges_t.dev_packed
+  size_t dev_packed_bytes = 0;
+  ~HostEdges() { if (dev_packed) cudaFree(dev_packed); }
 };
 const std::vector<double> &lgamma_table(size_t n);
 void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,

@@ -563,6 +563,21 @@ k_filter_recomb(const uint32_t *__restrict__ dvals, uint64_t e0, uint64_t e1, co
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
   if (lane == 0) filt[e] = kept;
 }
+// compact device-resident copy of the edge columns (tracs_edges_t.dev_packed)
+__global__ void k_pack_edges(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ dvals, const uint64_t *__restrict__ ncomp,
+                             const double *__restrict__ p0, const double *__restrict__ eK, uint64_t E, uint8_t *__restrict__ out) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  uint32_t *u = reinterpret_cast<uint32_t *>(out);
+  double *f = reinterpret_cast<double *>(out + 16 * E);
+  const uint64_t k = keys[e];
+  u[e] = (uint32_t)(k >> 32);
+  u[E + e] = (uint32_t)k;
+  u[2 * E + e] = dvals[e];
+  u[3 * E + e] = ncomp ? (uint32_t)ncomp[e] : 0u;
+  f[e] = p0 ? p0[e] : 0.0;
+  f[E + e] = eK ? eK[e] : 0.0;
+}
 __global__ void k_widen(const uint32_t *__restrict__ in, uint64_t E, uint64_t *__restrict__ out) {
   const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < E) out[e] = in[e];
@@ -1045,6 +1060,16 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       S.kernel_launches += 5;
       TRACS_CK(cudaGetLastError());
       S.ms_trans += T.stop();
+    }
+    if (o.keep_on_device && bands.size() == 1) {
+      void *dp = nullptr;
+      TRACS_CK(cudaMalloc(&dp, std::max<size_t>(32, 32 * E)));
+      out.dev_packed = dp;
+      out.dev_packed_bytes = 32 * E;
+      k_pack_edges<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, o.filter ? d_filt32.p : dv2.p, want_n ? d_nc.p : nullptr,
+                                                               fuse_trans ? d_p0.p : nullptr, fuse_trans ? d_eK.p : nullptr, E,
+                                                               (uint8_t *)dp);
+      S.kernel_launches++;
     }
     const size_t old = out.rows.size();
     T.start();

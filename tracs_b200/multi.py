@@ -47,6 +47,13 @@ def merge_by_rowblock(parts, world):
     return out
 
 
+class _DevBytes:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface v2)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
 class EdgeGather:
     """Reusable gather: keeps its pinned / device staging buffers between steps."""
 
@@ -71,6 +78,9 @@ class EdgeGather:
         cnts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
         dist.all_gather(cnts, cnt)
         cnts = [int(c.item()) for c in cnts]
+        dp = res.get("dev_packed") if hasattr(res, "get") else None
+        if dp is not None and self.device.type == "cuda":
+            return self._gather_device(res, dp, cnts, merge)
         mx = max(cnts + [1])
         nbytes = _BYTES_PER_EDGE * mx
         self.send = self._host(nbytes, self.send)
@@ -92,13 +102,99 @@ class EdgeGather:
         for r, b in enumerate(bufs):
             flat[r * nbytes:(r + 1) * nbytes].copy_(b, non_blocking=True)
         if self.device.type == "cuda":
-            torch.cuda.synchronize(self.device)
+            torch.cuda.current_stream(self.device).synchronize()
         host = flat.numpy()
         parts = []
         for r in range(self.world):
             secs = _sections(host[r * nbytes:(r + 1) * nbytes], mx)
             parts.append({c: s[:cnts[r]] for c, s in zip(COLUMNS, secs)})
         return merge_by_rowblock(parts, self.world) if merge else parts
+
+
+def _gather_device_impl(self, res, dp, cnts, merge):
+    """GPU-to-GPU path: every rank sends its packed device block (tracs_edges_t.dev_packed) straight to
+    rank 0 with exact sizes; rank 0 makes ONE device->host copy per rank into its pinned buffer."""
+    torch, dist = self.torch, self.dist
+    ptr, nbytes = dp
+    mine = torch.as_tensor(_DevBytes(ptr, max(nbytes, 1)), device=self.device)[:nbytes] if nbytes else torch.empty(0, dtype=torch.uint8, device=self.device)
+    if self.rank != 0:
+        if nbytes:
+            dist.send(mine, dst=0)
+        return None
+    bufs = [mine] + [torch.empty(_BYTES_PER_EDGE * cnts[r], dtype=torch.uint8, device=self.device) for r in range(1, self.world)]
+    reqs = [dist.irecv(bufs[r], src=r) for r in range(1, self.world) if cnts[r]]
+    for q in reqs:
+        q.wait()
+    total = _BYTES_PER_EDGE * sum(cnts)
+    self.recv = self._host(total, self.recv)
+    off, spans = 0, []
+    for r in range(self.world):
+        nb = _BYTES_PER_EDGE * cnts[r]
+        if nb:
+            self.recv[off:off + nb].copy_(bufs[r], non_blocking=True)
+        spans.append((off, nb))
+        off += nb
+    torch.cuda.current_stream(self.device).synchronize()
+    host = self.recv.numpy()
+    parts = []
+    for r, (o, nb) in enumerate(spans):
+        secs = _sections(host[o:o + nb], cnts[r])
+        parts.append({c: s for c, s in zip(COLUMNS, secs)})
+    return merge_by_rowblock(parts, self.world) if merge else parts
+
+
+EdgeGather._gather_device = _gather_device_impl
+
+
+class PipelinedGather:
+    """Runs EdgeGather on a worker thread and its own CUDA stream, so the gather of step k overlaps the
+    sweep of step k+1 (the library call releases the GIL). submit() per step, drain() before the
+    clock stops; results come back in submission order."""
+
+    def __init__(self, torch, dist, device, rank, world, merge):
+        import queue
+        import threading
+        self.g = EdgeGather(torch, dist, device, rank, world)
+        self.torch, self.device, self.merge = torch, device, merge
+        self.q = queue.Queue()
+        self.out = []
+        self.err = None
+        self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        torch = self.torch
+        if self.stream is not None:
+            torch.cuda.set_device(self.device)
+        while True:
+            item = self.q.get()
+            if item is None:
+                self.q.task_done()
+                return
+            try:
+                if self.stream is not None:
+                    with torch.cuda.stream(self.stream):
+                        self.out.append(self.g.gather(item, merge=self.merge))
+                else:
+                    self.out.append(self.g.gather(item, merge=self.merge))
+            except Exception as ex:  # surfaced by drain()
+                self.err = ex
+            self.q.task_done()
+
+    def submit(self, res):
+        self.q.put(res)
+
+    def drain(self):
+        self.q.join()
+        if self.err is not None:
+            raise self.err
+        out, self.out = self.out, []
+        return out
+
+    def close(self):
+        self.q.put(None)
+        self.t.join(timeout=30)
 
 
 def gather_edges(res, rank, world, dist, torch, device, merge=True):
