@@ -143,6 +143,20 @@ int tracs_calculate_posteriors(const double *counts, size_t rows, size_t cols, c
 int tracs_min_over_refs(const uint64_t *a, const uint64_t *b, const double *val, size_t n, uint64_t *out_a,
                         uint64_t *out_b, double *out_val, size_t *n_out);
 
+/* ---- site-sharded multi-GPU sweep (alignments larger than one GPU) ------------------------------
+ * d(i,j) and |N_i u N_j| are sums over disjoint site ranges, so rank r of R ingests only the column
+ * slab [L*r/R, L*(r+1)/R) of every sequence (dev_slab[n][pitch], L_slab sites), prefilters its share
+ * of the triangle row-blocks (opts->shard_rank/shard_world, opts->dist < 2048) and returns the
+ * candidate pairs it could not reject (device array of keys i<<32|j, sorted; owned by the handle).
+ * The caller all-gathers the candidate lists, calls tracs_site_shard_partials on every rank with the
+ * full list (device pointers; outputs: this slab's mismatch count and |N_i u N_j| per candidate),
+ * sums the two vectors over ranks (all-reduce) and keeps d <= dist; compared sites = L - union.
+ * Same quantities as src/pairsnp.hpp:398-403,417-419. tracs_b200/sites.py drives this with NCCL. */
+int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size_t pitch, const tracs_opts_t *opts,
+                          void **handle, const uint64_t **dev_cand_keys, size_t *n_cand);
+int tracs_site_shard_partials(void *handle, const uint64_t *dev_keys, size_t n_keys, uint32_t *dev_d, uint32_t *dev_union);
+int tracs_site_shard_close(void *handle);
+
 const char *tracs_last_error(void);
 int tracs_last_stats(tracs_stats_t *out);
 int tracs_device_count(void);
@@ -165,6 +179,8 @@ typedef struct tracs_synth {
   double gc;
   uint32_t n_days; /* days drawn uniformly from [0, n_days)              */
   uint32_t gaps;   /* number of '-' runs of length L/1000 per sample     */
+  uint64_t site_offset; /* generate columns [site_offset, site_offset + L) of an alignment of L_total sites */
+  uint64_t L_total;     /* 0 = L (whole alignment)                                                        */
 } tracs_synth_t;
 int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev_days);
 

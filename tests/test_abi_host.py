@@ -34,7 +34,7 @@ def test_struct_layouts_match_c():
     assert C.sizeof(_lib.Edges) == 14 * 8
     assert C.sizeof(_lib.Stats) == 12 * 8 + 10 * 4
     assert C.sizeof(_lib.Opts) == 8 + 16 + 16 + 8 + 24 + 8
-    assert C.sizeof(_lib.Synth) == 32 + 8 + 8 + 32 + 8
+    assert C.sizeof(_lib.Synth) == 32 + 8 + 8 + 32 + 8 + 16
 
 
 def test_no_gpu_fails_loudly():

@@ -206,3 +206,64 @@ def test_device_packed_columns_match_host():
     for c in ("rows", "cols", "dist", "ncomp"):
         assert secs[c].astype(np.uint64).tolist() == res[c].tolist()
     assert np.array_equal(secs["p0_log"], res["p0_log"]) and np.array_equal(secs["eK"], res["eK"])
+
+
+def _site_sharded_local(torch, s, world, dist):
+    """Emulates R ranks of the site-sharded sweep on one GPU (collectives replaced by torch ops)."""
+    import ctypes as C
+    from tracs_b200 import sites, _lib
+    n, L = s.shape
+    dev = torch.device("cuda")
+    slabs, handles, cands = [], [], []
+    for r in range(world):
+        lo, hi = sites.slab_bounds(L, r, world)
+        Ls = hi - lo
+        pitch = max(128, (Ls + 127) // 128 * 128)
+        buf = torch.full((n, pitch), ord("N"), dtype=torch.uint8, device=dev)
+        if Ls:
+            buf[:, :Ls] = torch.from_numpy(np.ascontiguousarray(s[:, lo:hi])).to(dev)
+        slabs.append(buf)
+        h, kptr, cnt, st = sites.open_shard(buf.data_ptr(), n, Ls, pitch, dist, r, world)
+        handles.append(h)
+        cands.append(torch.as_tensor(sites._Dev(kptr, cnt * 8), device=dev).view(torch.int64).clone() if cnt
+                     else torch.empty(0, dtype=torch.int64, device=dev))
+    keys, _ = torch.sort(torch.cat(cands))
+    E = keys.numel()
+    d = torch.zeros(max(E, 1), dtype=torch.int32, device=dev)
+    u = torch.zeros(max(E, 1), dtype=torch.int32, device=dev)
+    for h in handles:
+        dr, ur = torch.zeros_like(d), torch.zeros_like(u)
+        if E:
+            _lib.check(_lib.lib().tracs_site_shard_partials(h, C.c_void_p(keys.data_ptr()), E, C.c_void_p(dr.data_ptr()), C.c_void_p(ur.data_ptr())))
+        d += dr
+        u += ur
+        _lib.lib().tracs_site_shard_close(h)
+    keep = d[:E] <= dist
+    k = keys[:E][keep].cpu().numpy().astype(np.uint64)
+    return (k >> np.uint64(32), k & np.uint64(0xFFFFFFFF), d[:E][keep].cpu().numpy().astype(np.uint64),
+            (L - u[:E][keep].cpu().numpy().astype(np.int64)).astype(np.uint64), E)
+
+
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_site_sharded_equals_oracle(oracle_mod, world):
+    import torch
+    s = synth.generate(420, 150_000, p_var=0.06, n_clusters=50, mu=4, p_N=0.002, p_amb=0.01, seed=71)
+    for dist in (0, 25):
+        rows, cols, d, nn, n_cand = _site_sharded_local(torch, s, world, dist)
+        r, c, od, f, onn = oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4)
+        assert rows.tolist() == r.tolist() and cols.tolist() == c.tolist()
+        assert d.tolist() == od.tolist() and nn.tolist() == onn.tolist()
+        assert n_cand < 0.2 * 420 * 419 / 2
+
+
+def test_synth_slabs_are_columns_of_the_whole():
+    import torch
+    n, L = 64, 10_000
+    kw = dict(seed=5, p_var=0.05, n_clusters=4, mu=3.0, p_N=0.01, p_amb=0.02, gc=0.4)
+    whole = torch.empty((n, 10_112), dtype=torch.uint8, device="cuda")
+    tracs_b200.synth_device(whole.data_ptr(), n, L, 10_112, **kw)
+    for lo, hi in ((0, 3840), (3840, 7680), (7680, 10_000)):
+        pitch = (hi - lo + 127) // 128 * 128
+        slab = torch.empty((n, pitch), dtype=torch.uint8, device="cuda")
+        tracs_b200.synth_device(slab.data_ptr(), n, hi - lo, pitch, site_offset=lo, L_total=L, **kw)
+        assert torch.equal(slab[:, :hi - lo], whole[:, lo:hi])

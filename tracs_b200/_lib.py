@@ -41,7 +41,7 @@ class Opts(C.Structure):
 class Synth(C.Structure):
     _fields_ = [("n", C.c_uint64), ("L", C.c_uint64), ("pitch", C.c_uint64), ("seed", C.c_uint64), ("p_var", C.c_double),
                 ("n_clusters", C.c_uint32), ("mu", C.c_double), ("p_N", C.c_double), ("p_amb", C.c_double),
-                ("gc", C.c_double), ("n_days", C.c_uint32), ("gaps", C.c_uint32)]
+                ("gc", C.c_double), ("n_days", C.c_uint32), ("gaps", C.c_uint32), ("site_offset", C.c_uint64), ("L_total", C.c_uint64)]
 
 
 # every symbol include/tracs_b200.h declares
@@ -49,7 +49,8 @@ SYMBOLS = ["tracs_pairsnp", "tracs_pairsnp_host", "tracs_pairsnp_device", "tracs
            "tracs_lprob_k_given_N", "tracs_calculate_posteriors", "tracs_min_over_refs", "tracs_last_error",
            "tracs_last_stats", "tracs_device_count", "tracs_trim", "tracs_set_device", "tracs_synth_device", "tracs_dev_alloc",
            "tracs_dev_free", "tracs_host_alloc_pinned", "tracs_host_free_pinned", "tracs_memcpy_d2h",
-           "tracs_memcpy_h2d", "tracs_int_peak", "tracs_read_fasta", "tracs_free_fasta", "tracs_shard_rowblocks"]
+           "tracs_memcpy_h2d", "tracs_int_peak", "tracs_read_fasta", "tracs_free_fasta", "tracs_shard_rowblocks",
+           "tracs_site_shard_open", "tracs_site_shard_partials", "tracs_site_shard_close"]
 
 _lib = None
 
@@ -84,6 +85,10 @@ def lib():
                                        C.POINTER(C.POINTER(C.c_char_p))]
         L.tracs_free_fasta.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_char_p), C.c_size_t]
         L.tracs_free_fasta.restype = None
+        L.tracs_site_shard_open.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Opts), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.tracs_site_shard_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.tracs_site_shard_close.argtypes = [C.c_void_p]
         L.tracs_shard_rowblocks.argtypes = [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib

@@ -119,8 +119,11 @@ def min_over_refs(a, b, val):
 
 
 def synth_device(dev_ptr, n, L, pitch, seed=1, p_var=0.01, n_clusters=20, mu=5.0, p_N=1e-3, p_amb=0.0, gc=0.5, n_days=180,
-                 gaps=2, dev_days=None):
-    cfg = _lib.Synth(n, L, pitch, seed, p_var, n_clusters, mu, p_N, p_amb, gc, n_days, gaps)
+                 gaps=2, dev_days=None, site_offset=0, L_total=0):
+    """Seeded synthetic alignment written straight into device memory. With site_offset / L_total the
+    buffer receives the column slab [site_offset, site_offset + L) of an L_total-site alignment
+    (identical bytes to the corresponding columns of the whole alignment)."""
+    cfg = _lib.Synth(n, L, pitch, seed, p_var, n_clusters, mu, p_N, p_amb, gc, n_days, gaps, site_offset, L_total)
     _lib.check(_lib.lib().tracs_synth_device(C.byref(cfg), C.c_void_p(dev_ptr), C.c_void_p(dev_days) if dev_days else None))
 
 

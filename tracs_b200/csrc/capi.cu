@@ -102,30 +102,12 @@ void host_pool_free(void *p) {
   free(p);
 }
 
-static void require_device() {
+void require_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
     throw std::runtime_error(std::string("tracs_b200: no CUDA device available (") + cudaGetErrorString(e) +
                              "); this library has no CPU fallback");
-}
-
-template <typename F>
-static int guarded(F &&f) {
-  try {
-    f();
-    return 0;
-  } catch (const CudaError &e) {
-    set_error(e.msg);
-    cudaGetLastError();
-    return 2;
-  } catch (const std::out_of_range &e) {
-    set_error(e.what());
-    return 3;
-  } catch (const std::exception &e) {
-    set_error(e.what());
-    return 1;
-  }
 }
 
 template <typename T>
@@ -192,6 +174,7 @@ struct SynthDev {
   uint32_t thr_var24, thr_found16, thr_gc16, n_clusters;
   uint32_t thr_priv32, thr_N32, thr_amb16, n_days, gaps;
   uint64_t gap_len;
+  uint64_t site_offset, L_total;  // this buffer holds columns [site_offset, site_offset + L) of L_total
 };
 __global__ void k_synth(SynthDev c, uint8_t *__restrict__ seqs) {
   const uint64_t chunks = c.pitch / 16;
@@ -201,7 +184,7 @@ __global__ void k_synth(SynthDev c, uint8_t *__restrict__ seqs) {
   const uint32_t cluster = (uint32_t)(mix64(c.seed * 0x100000001b3ull + 0x51ull + s) % c.n_clusters);
   uint64_t g0[4] = {~0ull, ~0ull, ~0ull, ~0ull};
   for (uint32_t r = 0; r < c.gaps && r < 4; ++r)
-    if (c.L > c.gap_len) g0[r] = mix64(c.seed ^ (0xabcdefull + s * 8 + r)) % (c.L - c.gap_len);
+    if (c.L_total > c.gap_len) g0[r] = mix64(c.seed ^ (0xabcdefull + s * 8 + r)) % (c.L_total - c.gap_len);
   const char B[4] = {'A', 'C', 'G', 'T'};
   // 2-base IUPAC codes indexed [b][o]
   const char AMB[4][4] = {{'A', 'M', 'R', 'W'}, {'M', 'C', 'S', 'Y'}, {'R', 'S', 'G', 'K'}, {'W', 'Y', 'K', 'T'}};
@@ -209,9 +192,10 @@ __global__ void k_synth(SynthDev c, uint8_t *__restrict__ seqs) {
   for (int q = 0; q < 4; ++q) {
     uint32_t w = 0;
     for (int t = 0; t < 4; ++t) {
-      const uint64_t site = ch * 16 + q * 4 + t;
+      const uint64_t lsite = ch * 16 + q * 4 + t;
+      const uint64_t site = c.site_offset + lsite;  // every random draw is keyed on the GLOBAL site
       char chv = 'N';
-      if (site < c.L) {
+      if (lsite < c.L) {
         const uint64_t hs = mix64(c.seed * 0x9E3779B97F4A7C15ull + site);
         uint32_t b;
         if ((hs & 0xFFFFu) < c.thr_gc16) b = ((hs >> 60) & 1) ? 1u : 2u; else b = ((hs >> 60) & 1) ? 0u : 3u;
@@ -226,7 +210,7 @@ __global__ void k_synth(SynthDev c, uint8_t *__restrict__ seqs) {
           if (((hp >> 40) & 0xFFFFu) < c.thr_amb16) { amb = true; other = (b + 1 + (uint32_t)((hp >> 56) % 3)) & 3u; }
         }
         chv = amb ? AMB[b][other] : B[b];
-        const uint64_t hn = mix64((c.seed + 0x7777ull) * 0xC2B2AE3D27D4EB4Full + s * c.L + site);
+        const uint64_t hn = mix64((c.seed + 0x7777ull) * 0xC2B2AE3D27D4EB4Full + s * c.L_total + site);
         if ((uint32_t)hn < c.thr_N32) chv = 'N';
         for (int r = 0; r < 4; ++r) if (site >= g0[r] && site - g0[r] < c.gap_len) chv = '-';
       }
@@ -583,12 +567,15 @@ int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev
     c.thr_found16 = (uint32_t)(0.3 * 65536.0);
     c.thr_gc16 = (uint32_t)(clamp01(cfg->gc) * 65536.0);
     c.n_clusters = std::max(1u, cfg->n_clusters);
-    const double v = std::max(1.0, cfg->p_var * (double)cfg->L);
+    c.site_offset = cfg->site_offset;
+    c.L_total = cfg->L_total ? cfg->L_total : cfg->L;
+    if (c.site_offset + c.L > c.L_total) throw std::runtime_error("synth: slab exceeds L_total");
+    const double v = std::max(1.0, cfg->p_var * (double)c.L_total);
     c.thr_priv32 = (uint32_t)std::min(4294967295.0, clamp01(cfg->mu / v) * 4294967296.0);
     c.thr_N32 = (uint32_t)std::min(4294967295.0, clamp01(cfg->p_N) * 4294967296.0);
     c.thr_amb16 = (uint32_t)(clamp01(cfg->p_amb) * 65536.0);
     c.n_days = cfg->n_days; c.gaps = cfg->gaps;
-    c.gap_len = cfg->L / 1000;
+    c.gap_len = c.L_total / 1000;
     const uint64_t total = c.n * (c.pitch / 16);
     if (total) {
       k_synth<<<(unsigned)((total + 255) / 256), 256>>>(c, dev_seqs);

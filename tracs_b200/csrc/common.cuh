@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,27 @@ struct CudaError {
 // Keeps freed blocks in the default memory pool instead of returning them to the driver, so the
 // multi-GB scratch buffers of one call are reused by the next (tracs_trim() releases them).
 void pool_init();
+
+void require_device();  // throws unless a CUDA device is usable (there is no CPU fallback)
+
+// C-ABI status codes: 0 ok, 1 runtime error, 2 CUDA error, 3 index/range error
+template <typename F>
+static int guarded(F &&f) {
+  try {
+    f();
+    return 0;
+  } catch (const CudaError &e) {
+    set_error(e.msg);
+    cudaGetLastError();
+    return 2;
+  } catch (const std::out_of_range &e) {
+    set_error(e.what());
+    return 3;
+  } catch (const std::exception &e) {
+    set_error(e.what());
+    return 1;
+  }
+}
 
 // RAII device buffer
 template <typename T>

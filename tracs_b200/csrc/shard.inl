@@ -1,0 +1,196 @@
+// Site-sharded multi-GPU sweep (included at the end of sweep.cu: same translation unit as k_sweep).
+//
+// Every quantity of the path is ADDITIVE over disjoint site ranges: d(i,j) = sum_r d_r(i,j) and
+// |N_i u N_j| = sum_r |N_i u N_j|_r. So for alignments too large for one GPU (C3: 100 000 x 2 Mb =
+// 200 GB of ASCII) rank r ingests only the column slab [L*r/R, L*(r+1)/R) of every sequence and
+//   1. prefilters ITS share of the triangle row-blocks with the tile kernel on its own first words
+//      (a partial distance over any subset of sites is a lower bound of d, so pairs it rejects are
+//      decided for good);                                              -> candidate pairs (few)
+//   2. the candidate lists are all-gathered (the caller does this with NCCL);
+//   3. every rank evaluates its slab's partial d and |N_i u N_j| for ALL candidates;  [this file]
+//   4. the two integer vectors are all-reduced (sum) and thresholded by the caller.
+// No bit-plane or N-plane ever crosses NVLink; traffic is O(candidates).
+// Reference semantics unchanged: src/pairsnp.hpp:398-403 (d), :417-419 (compared sites).
+
+namespace tracs {
+
+struct SiteShard {
+  Ingested ing;
+  DevBuf<uint64_t> cand;   // candidate keys (i << 32 | j) found by this rank, sorted
+  uint64_t n_cand = 0;
+};
+
+// one warp per candidate: mismatches over ALL local words, and |N_i u N_j| over the local slab
+__global__ void __launch_bounds__(256)
+k_shard_partials(const uint64_t *__restrict__ keys, uint64_t n_keys, const uint4 *__restrict__ planesT, uint32_t Wp,
+                 const uint32_t *__restrict__ nplane, uint64_t npitch, const uint8_t *__restrict__ nsum, uint64_t spitch,
+                 const uint32_t *__restrict__ ncount, uint32_t *__restrict__ d_out, uint32_t *__restrict__ u_out) {
+  const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (e >= n_keys) return;
+  const uint64_t k = keys[e];
+  const uint64_t i = k >> 32, j = k & 0xFFFFFFFFull;
+  const uint4 *ri = planesT + i * Wp, *rj = planesT + j * Wp;
+  uint32_t mism = 0;
+#pragma unroll 4
+  for (uint32_t w = lane; w < Wp; w += 32) {
+    const uint4 x = __ldg(ri + w), y = __ldg(rj + w);
+    mism += __popc(~((x.x & y.x) | (x.y & y.y) | (x.z & y.z) | (x.w & y.w)));
+  }
+  const uint32_t *si = reinterpret_cast<const uint32_t *>(nsum + i * spitch);
+  const uint32_t *sj = reinterpret_cast<const uint32_t *>(nsum + j * spitch);
+  const uint4 *ni = reinterpret_cast<const uint4 *>(nplane + i * npitch);
+  const uint4 *nj = reinterpret_cast<const uint4 *>(nplane + j * npitch);
+  uint32_t inter = 0;
+  for (uint64_t q = lane; q < spitch / 4; q += 32) {
+    uint32_t m = __ldg(si + q) & __ldg(sj + q);
+    while (m) {
+      const uint32_t b = __ffs(m) - 1;
+      m &= m - 1;
+      const uint4 x = __ldg(ni + q * 32 + b), y = __ldg(nj + q * 32 + b);
+      inter += __popc(x.x & y.x) + __popc(x.y & y.y) + __popc(x.z & y.z) + __popc(x.w & y.w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mism += __shfl_xor_sync(0xFFFFFFFFu, mism, o);
+    inter += __shfl_xor_sync(0xFFFFFFFFu, inter, o);
+  }
+  if (lane == 0) {
+    d_out[e] = mism;
+    u_out[e] = ncount[i] + ncount[j] - inter;
+  }
+}
+
+}  // namespace tracs
+
+using namespace tracs;
+
+extern "C" {
+
+int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size_t pitch, const tracs_opts_t *opts,
+                          void **handle, const uint64_t **dev_cand_keys, size_t *n_cand) {
+  *handle = nullptr;
+  *dev_cand_keys = nullptr;
+  *n_cand = 0;
+  memset(&g_stats, 0, sizeof g_stats);
+  return guarded([&] {
+    require_device();
+    if (!opts) throw std::runtime_error("site shard: options required");
+    const tracs_opts_t &o = *opts;
+    if (o.dist < 0 || (uint64_t)o.dist >= (uint64_t)PREFILTER_WORDS * 32)
+      throw std::runtime_error("site-sharded sweep needs a SNP threshold in [0, 2048): it relies on the prefilter");
+    if (o.filter) throw std::runtime_error("site-sharded sweep does not run the recombination filter");
+    if (n == 0 || n >= (1ull << 31)) throw std::runtime_error("site shard: bad sample count");
+    cudaStream_t st = 0;
+    Timer T(st), Ttot(st);
+    Ttot.start();
+    std::unique_ptr<SiteShard> sh(new SiteShard());
+    g_stats.n_samples = n;
+    g_stats.seq_length = L_slab;
+    ingest_device(dev_slab, n, L_slab, pitch, true, false, sh->ing, st);
+    const Ingested &g = sh->ing;
+    const uint64_t i_end = (o.i_end == 0 || o.i_end > n) ? n : o.i_end;
+    const int world = std::max(1, (int)o.shard_world), rank = std::max(0, (int)o.shard_rank);
+    const TilePlan plan = plan_tiles(n, i_end, o.j_start, g.Npad, rank, world);
+    // all of this rank's row-blocks append to ONE candidate list; launches are cut so that the tile
+    // count stays in 32 bits, the list capacity bounds the (few) survivors
+    const uint64_t CAND_CAP = 1ull << 26;
+    DevBuf<uint64_t> keys(CAND_CAP), keys2(CAND_CAP);
+    DevBuf<uint32_t> dv(CAND_CAP), dv2(CAND_CAP);
+    DevBuf<unsigned long long> counter(1);
+    TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+    static bool attr_set = false;
+    if (!attr_set) {
+      TRACS_CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+      attr_set = true;
+    }
+    int dev = 0, n_sm = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, SWEEP_THREADS, SWEEP_SMEM);
+    occ = std::max(1, occ);
+    const uint32_t words = std::min<uint32_t>(PREFILTER_WORDS, g.Wp);  // Wp is a multiple of KC
+    DevBuf<uint32_t> d_rb(std::max<size_t>(1, plan.my_rb.size())), d_prefix(plan.my_rb.size() + 1);
+    size_t k0 = 0;
+    T.start();
+    while (k0 < plan.my_rb.size()) {
+      std::vector<uint32_t> rbs, prefix{0};
+      uint64_t tiles = 0, pairs = 0;
+      size_t k1 = k0;
+      while (k1 < plan.my_rb.size() && tiles < (1ull << 30)) {
+        tiles += plan.n_cb - std::max(plan.my_rb[k1], plan.cb_min);
+        pairs += plan.rb_pairs[k1];
+        rbs.push_back(plan.my_rb[k1]);
+        prefix.push_back((uint32_t)tiles);
+        ++k1;
+      }
+      TRACS_CK(cudaMemcpyAsync(d_rb.p, rbs.data(), rbs.size() * 4, cudaMemcpyHostToDevice, st));
+      TRACS_CK(cudaMemcpyAsync(d_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, st));
+      SweepArgs a;
+      a.planes = g.planes.p; a.Wp = words; a.Npad = g.Npad; a.n = (uint32_t)n; a.i_end = (uint32_t)i_end;
+      a.j_start = (uint32_t)o.j_start; a.dist = o.dist; a.rb_list = d_rb.p; a.tile_prefix = d_prefix.p;
+      a.n_rb = (uint32_t)rbs.size(); a.n_tiles = (uint32_t)tiles; a.cb_min = plan.cb_min; a.counter = counter.p;
+      a.keys = keys.p; a.dvals = dv.p; a.cap = CAND_CAP; a.one = 1;
+      const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)n_sm * occ);
+      if (grid) {
+        k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
+        g_stats.kernel_launches++;
+        TRACS_CK(cudaGetLastError());
+      }
+      TRACS_CK(cudaStreamSynchronize(st));  // rbs/prefix are reused by the next cut
+      g_stats.n_tiles += tiles;
+      g_stats.n_pairs += pairs;
+      g_stats.swept_wordpairs += pairs * words;
+      k0 = k1;
+    }
+    g_stats.ms_sweep += T.stop();
+    unsigned long long nc = 0;
+    TRACS_CK(cudaMemcpyAsync(&nc, counter.p, sizeof nc, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaStreamSynchronize(st));
+    if (nc > CAND_CAP)
+      throw std::runtime_error("site-sharded sweep: the prefilter left too many candidate pairs; use the single-GPU / tile-sharded path");
+    g_stats.n_candidates = nc;
+    if (nc) {
+      T.start();
+      int end_bit = 32;
+      while ((1ull << (end_bit - 32)) < n) end_bit++;
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, keys2.p, dv.p, dv2.p, (int64_t)nc, 0, end_bit, st);
+      DevBuf<uint8_t> tmp(tb);
+      cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys2.p, dv.p, dv2.p, (int64_t)nc, 0, end_bit, st);
+      g_stats.kernel_launches += 2 + (end_bit + 7) / 8;
+      sh->cand.alloc(nc);
+      TRACS_CK(cudaMemcpyAsync(sh->cand.p, keys2.p, nc * 8, cudaMemcpyDeviceToDevice, st));
+      TRACS_CK(cudaStreamSynchronize(st));
+      g_stats.ms_sort += T.stop();
+    }
+    sh->n_cand = nc;
+    g_stats.ms_total = Ttot.stop();
+    *dev_cand_keys = sh->cand.p;
+    *n_cand = nc;
+    *handle = sh.release();
+  });
+}
+
+int tracs_site_shard_partials(void *handle, const uint64_t *dev_keys, size_t n_keys, uint32_t *dev_d, uint32_t *dev_union) {
+  return guarded([&] {
+    if (!handle) throw std::runtime_error("site shard: null handle");
+    SiteShard *sh = (SiteShard *)handle;
+    const Ingested &g = sh->ing;
+    if (!n_keys) return;
+    Timer T(0);
+    T.start();
+    k_shard_partials<<<(unsigned)(((uint64_t)n_keys * 32 + 255) / 256), 256>>>(dev_keys, n_keys, g.planesT.p, g.Wp, g.nplane.p, g.npitch,
+                                                                            g.nsum.p, g.spitch, g.ncount.p, dev_d, dev_union);
+    g_stats.kernel_launches++;
+    TRACS_CK(cudaGetLastError());
+    g_stats.ms_refine += T.stop();
+  });
+}
+
+int tracs_site_shard_close(void *handle) {
+  return guarded([&] { delete (SiteShard *)handle; });
+}
+
+}  // extern "C"

@@ -16,12 +16,15 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <memory>
 #include <stdexcept>
 
 #include "common.cuh"
 #include "trans.cuh"
 
 namespace tracs {
+
+static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 // ------------------------------------------------------------------------------------------
 // base-mask table: bit0=A bit1=C bit2=G bit3=T ; everything that is not an IUPAC code = 15
@@ -681,32 +684,36 @@ __global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
-static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 
-// Sweeps the device-resident ASCII matrix and appends edges (sorted) to `out`.
-void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,
-                  HostEdges &out, cudaStream_t st) {
+// Everything the ingest stage leaves in device memory for one alignment (or one site slab of it).
+struct Ingested {
+  uint64_t n = 0, L = 0;
+  uint64_t npitch = 0, spitch = 0;     // N-plane row pitch (words) / summary row pitch (bytes)
+  uint64_t V = 0, W = 0;               // variable sites, 32-site words
+  uint32_t Wp = KC, Npad = 0;          // padded words / samples
+  DevBuf<uint32_t> nplane, ncount, site_idx;
+  DevBuf<uint8_t> nsum;
+  DevBuf<uint4> planes, planesT;
+};
+
+// ASCII matrix (device) -> N-plane + summaries + variable-site bit-planes (K0a + K0b)
+static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, bool want_n, bool keep_site_idx,
+                          Ingested &g, cudaStream_t st) {
   tracs_stats_t &S = g_stats;
-  S.n_samples = n;
-  S.seq_length = L;
-  const uint64_t i_end = std::min<uint64_t>(o.i_end, n);
-  const uint64_t j_start = o.j_start;
-  if (n == 0 || i_end == 0 || j_start >= n) return;
-  if (n >= (1ull << 31)) throw std::runtime_error("too many samples");
   if (pitch % 32 != 0 || pitch < round_up(L, 32)) throw std::runtime_error("device alignment pitch must be a multiple of 32 and >= L rounded up to 32");
-
-  Timer T(st), Ttot(st);
-  Ttot.start();
-
+  Timer T(st);
+  g.n = n;
+  g.L = L;
   // ---- K0a ---------------------------------------------------------------------------
   const uint64_t Lw = (L + 31) / 32;                       // words with sites
   const uint64_t npitch = std::max<uint64_t>(32, round_up(Lw, 32));  // N-plane row pitch in words (whole warps)
   const uint64_t spitch = round_up(npitch / 32, 4);        // summary bytes per row (uint32 granules)
+  g.npitch = npitch;
+  g.spitch = spitch;
   DevBuf<uint32_t> colmask(std::max<uint64_t>(1, Lw * 4));
-  DevBuf<uint32_t> nplane, ncount;
-  DevBuf<uint8_t> nsum;
-  const bool want_n = o.want_ncomp != 0;
+  DevBuf<uint32_t> &nplane = g.nplane, &ncount = g.ncount;
+  DevBuf<uint8_t> &nsum = g.nsum;
   // N-plane is always produced by k_pack (same pass over the ASCII bytes)
   nplane.alloc(n * npitch);
   nsum.alloc(n * spitch);
@@ -732,12 +739,12 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     TRACS_CK(cudaMemsetAsync(nplane.p, 0, nplane.n * sizeof(uint32_t), st));
     TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
   }
-  S.ms_pack = T.stop();
+  S.ms_pack += T.stop();
 
   // ---- K0b: variable sites -> planes -----------------------------------------------------
   T.start();
   uint64_t V = 0;
-  DevBuf<uint32_t> site_idx;
+  DevBuf<uint32_t> &site_idx = g.site_idx;
   if (L > 0) {
     DevBuf<uint8_t> flags(round_up(L, 8));
     k_siteflags<<<(unsigned)((Lw * 4 + 255) / 256), 256, 0, st>>>(colmask.p, L, flags.p);
@@ -756,41 +763,78 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   const uint64_t W = (V + 31) / 32;
   const uint32_t Wp = (uint32_t)std::max<uint64_t>(KC, round_up(W, KC));
   const uint32_t Npad = (uint32_t)round_up(n, TILE);
-  S.n_variable_sites = V;
-  S.n_words = Wp;
-  DevBuf<uint4> planes((size_t)Wp * Npad), planesT((size_t)Wp * n);
-  TRACS_CK(cudaMemsetAsync(planes.p, 0xFF, planes.n * sizeof(uint4), st));
-  TRACS_CK(cudaMemsetAsync(planesT.p, 0xFF, planesT.n * sizeof(uint4), st));
+  g.V = V; g.W = W; g.Wp = Wp; g.Npad = Npad;
+  S.n_variable_sites += V;
+  S.n_words += Wp;
+  g.planes.alloc((size_t)Wp * Npad);
+  g.planesT.alloc((size_t)Wp * n);
+  TRACS_CK(cudaMemsetAsync(g.planes.p, 0xFF, g.planes.n * sizeof(uint4), st));
+  TRACS_CK(cudaMemsetAsync(g.planesT.p, 0xFF, g.planesT.n * sizeof(uint4), st));
   if (W > 0) {
     const uint32_t schunk = 512;
     dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
-    k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, planes.p, Npad, planesT.p, Wp, schunk);
+    k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, g.planes.p, Npad, g.planesT.p, Wp, schunk);
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
   }
-  S.ms_compact = T.stop();
-  if (!o.filter) site_idx.release();
+  S.ms_compact += T.stop();
+  if (!keep_site_idx) site_idx.release();
+}
 
-  // ---- tile lists ------------------------------------------------------------------------
+// which row-blocks a shard sweeps, and how many pairs each holds
+struct TilePlan {
+  uint32_t n_cb = 0, cb_min = 0;
+  std::vector<uint32_t> my_rb;
+  std::vector<uint64_t> rb_pairs;
+};
+static TilePlan plan_tiles(uint64_t n, uint64_t i_end, uint64_t j_start, uint32_t Npad, int rank, int world) {
+  TilePlan p;
   const uint32_t n_rb_all = (uint32_t)((i_end + TILE - 1) / TILE);
-  const uint32_t n_cb = Npad / TILE;
-  const uint32_t cb_min = (uint32_t)(j_start / TILE);
-  const int world = std::max(1, (int)o.shard_world), rank = std::max(0, (int)o.shard_rank);
+  p.n_cb = Npad / TILE;
+  p.cb_min = (uint32_t)(j_start / TILE);
   if (rank >= world) throw std::runtime_error("shard_rank >= shard_world");
   // row-blocks dealt boustrophedon (0..w-1, w-1..0, ...) so every shard gets equal triangle area
-  std::vector<uint32_t> my_rb;
   for (uint32_t rb = 0; rb < n_rb_all; ++rb) {
-    if (shard_owner(rb, world) == rank && std::max(rb, cb_min) < n_cb) my_rb.push_back(rb);
-  }
-  auto pairs_of_rb = [&](uint32_t rb) -> uint64_t {
+    if (shard_owner(rb, world) != rank || std::max(rb, p.cb_min) >= p.n_cb) continue;
     uint64_t tot = 0;
-    uint64_t r0 = (uint64_t)rb * TILE, r1 = std::min<uint64_t>(i_end, r0 + TILE);
+    const uint64_t r0 = (uint64_t)rb * TILE, r1 = std::min<uint64_t>(i_end, r0 + TILE);
     for (uint64_t i = r0; i < r1; ++i) {
-      uint64_t j0 = std::max<uint64_t>(j_start, i + 1);
+      const uint64_t j0 = std::max<uint64_t>(j_start, i + 1);
       if (j0 < n) tot += n - j0;
     }
-    return tot;
-  };
+    p.my_rb.push_back(rb);
+    p.rb_pairs.push_back(tot);
+  }
+  return p;
+}
+
+// Sweeps the device-resident ASCII matrix and appends edges (sorted) to `out`.
+void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,
+                  HostEdges &out, cudaStream_t st) {
+  tracs_stats_t &S = g_stats;
+  S.n_samples = n;
+  S.seq_length = L;
+  const uint64_t i_end = std::min<uint64_t>(o.i_end, n);
+  const uint64_t j_start = o.j_start;
+  if (n == 0 || i_end == 0 || j_start >= n) return;
+  if (n >= (1ull << 31)) throw std::runtime_error("too many samples");
+
+  Timer T(st), Ttot(st);
+  Ttot.start();
+  const bool want_n = o.want_ncomp != 0;
+  Ingested ing;
+  ingest_device(dev_seqs, n, L, pitch, want_n, o.filter != 0, ing, st);
+  const uint64_t npitch = ing.npitch, spitch = ing.spitch, V = ing.V, W = ing.W;
+  const uint32_t Wp = ing.Wp, Npad = ing.Npad;
+  DevBuf<uint32_t> &nplane = ing.nplane, &ncount = ing.ncount, &site_idx = ing.site_idx;
+  DevBuf<uint8_t> &nsum = ing.nsum;
+  DevBuf<uint4> &planes = ing.planes, &planesT = ing.planesT;
+
+  // ---- tile lists ------------------------------------------------------------------------
+  const int world = std::max(1, (int)o.shard_world), rank = std::max(0, (int)o.shard_rank);
+  const TilePlan plan = plan_tiles(n, i_end, j_start, Npad, rank, world);
+  const uint32_t n_cb = plan.n_cb, cb_min = plan.cb_min;
+  const std::vector<uint32_t> &my_rb = plan.my_rb;
   // bands: consecutive owned row-blocks whose pair count fits the edge buffer
   const uint64_t CAP_MAX = 1ull << 28;
   std::vector<std::pair<size_t, size_t>> bands;
@@ -799,7 +843,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     size_t b0 = 0;
     uint64_t acc = 0;
     for (size_t k = 0; k < my_rb.size(); ++k) {
-      uint64_t p = pairs_of_rb(my_rb[k]);
+      uint64_t p = plan.rb_pairs[k];
       S.n_pairs += p;
       if (k > b0 && acc + p > CAP_MAX) {
         bands.push_back({b0, k});
@@ -1099,3 +1143,5 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
 }
 
 }  // namespace tracs
+
+#include "shard.inl"
