@@ -38,6 +38,10 @@ import numpy as np
 WORKLOAD = dict(name="C2: 10000 seqs x 5 Mb E. coli-like, 1% variable sites, dist<=20, transcluster with dates",
                 n=10000, L=5_000_000, p_var=0.01, n_clusters=100, mu=5.0, p_N=1e-3, p_amb=0.0, gc=0.508, seed=2,
                 n_days=180, gaps=2, dist=20, lamb=29.903, beta=73.0, threshold_Ek=0.01)
+# BASELINE.json configs[2]: only reachable with the site-sharded multi-GPU mode (200 GB of ASCII)
+WORKLOAD_C3 = dict(name="C3: 100000 seqs x 2 Mb sparse alignment, 1% variable sites, dist<=20, site-sharded over the GPUs",
+                   n=100000, L=2_000_000, p_var=0.01, n_clusters=2000, mu=5.0, p_N=1e-3, p_amb=0.0, gc=0.5, seed=3,
+                   n_days=180, gaps=2, dist=20, lamb=29.903, beta=73.0, threshold_Ek=0.01)
 SECONDS_IN_YEAR = 31556952.0
 
 
@@ -204,6 +208,91 @@ def _emit(saved_fd, line):
     os.write(saved_fd, (json.dumps(line) + "\n").encode())
 
 
+def run_sites(args, saved_stdout, torch, tracs_b200, dist_mod, device, rank, world, local):
+    """Strong scaling of ONE alignment too large for a single GPU (BASELINE configs[2]): rank r holds the
+    column slab r of every sequence; see tracs_b200/sites.py for the exchange steps."""
+    from tracs_b200 import sites
+    w = dict(WORKLOAD_C3)
+    if args.n:
+        w["n"] = args.n
+        w["n_clusters"] = max(2, args.n // 50)
+    if args.L:
+        w["L"] = args.L
+    n, L = w["n"], w["L"]
+    P = n * (n - 1) // 2
+    lo, hi = sites.slab_bounds(L, rank, world)
+    Ls = hi - lo
+    pitch = max(128, (Ls + 127) // 128 * 128)
+    slab = torch.empty(n * pitch, dtype=torch.uint8, device=device)
+    d_days = torch.empty(n, dtype=torch.int32, device=device)
+    tracs_b200.synth_device(slab.data_ptr(), n, Ls, pitch, seed=w["seed"], p_var=w["p_var"], n_clusters=w["n_clusters"], mu=w["mu"],
+                            p_N=w["p_N"], p_amb=w["p_amb"], gc=w["gc"], n_days=w["n_days"], gaps=w["gaps"], dev_days=d_days.data_ptr(),
+                            site_offset=lo, L_total=L)
+    days = d_days.cpu().numpy()
+
+    def step():
+        return sites.sweep(torch, dist_mod, device, rank, world, slab.data_ptr(), n, Ls, pitch, L, w["dist"], days=days,
+                           lamb=w["lamb"], beta=w["beta"], threshold_Ek=w["threshold_Ek"])
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats = []
+    ev0.record()
+    for _ in range(args.steps):
+        res, st = step()
+        stats.append(st)
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist_mod.all_reduce(t_ms, op=dist_mod.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    if rank == 0:
+        def avg(k):
+            return float(np.mean([s_[k] for s_ in stats]))
+        peak = tracs_b200.int_peak()
+        peak_wp = min(peak["lop3_per_s"] / 4.0, peak["popc_per_s"])
+        wp = avg("swept_wordpairs")
+        roof = {"bound": "int_pipe", "kernel": "k_sweep", "what": "prefilter launch on this rank's row-blocks (first 64 local words)",
+                "achieved": wp * 6 / (avg("ms_sweep") * 1e-3) / 1e9, "peak": peak_wp * 6 / 1e9, "unit": "Ginstr/s",
+                "frac": (wp / (avg("ms_sweep") * 1e-3)) / peak_wp, "traffic": None, "ms_per_launch": avg("ms_sweep"),
+                "peak_source": "measured in this run (tracs_int_peak)"}
+        line = {
+            "metric": "site-pair comparisons/s (P*L/t)", "value": P * L / (ms_per_step * 1e-3), "unit": "site-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 bit-planes (int32 counts), f64 likelihood",
+            "data": "synthetic (device-generated ASCII column slabs, seeded)",
+            "config": {"workload": w["name"], "n": n, "L": L, "pairs": P, "edges": int(len(res["rows"])), "dist": w["dist"],
+                       "candidates": int(stats[-1]["n_candidates_all"]),
+                       "parallelism": "site-sharded: rank r ingests columns [L*r/R, L*(r+1)/R) of every sequence and prefilters its "
+                                      "row-blocks; candidates all-gathered, per-slab partial d and |N u N| all-reduced (NCCL)",
+                       "l2": "inputs (%.1f GB ASCII per GPU) larger than L2" % (n * pitch / 1e9)},
+            "clocks": clk, "gpu_launches": int(sum(s_["kernel_launches"] + 1 for s_ in stats)), "roofline": roof,
+            "stages_ms": {k: avg(k) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_sort", "ms_refine", "ms_total")},
+            "e2e": {"value": None, "unit": "site-pairs/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                    "note": "host-buffer e2e is measured on the N=1 C2 line"},
+            "cpu_baseline": {"value": None, "note": "timed at N=1 only"},
+        }
+        _emit(saved_stdout, line)
+    if world > 1:
+        dist_mod.barrier()
+        dist_mod.destroy_process_group()
+    return 0
+
+
 def main():
     saved_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -216,7 +305,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--shard", default="msa", choices=["msa", "tiles"], help="N>1: one MSA per GPU (weak) or row-blocks of one MSA (strong)")
+    ap.add_argument("--shard", default="msa", choices=["msa", "tiles", "sites"],
+                    help="N>1: one MSA per GPU (weak, default) | row-blocks of one MSA, ingest replicated (strong) | "
+                         "column slabs of the C3 alignment per GPU (strong; the only mode that fits 100k x 2 Mb)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, saved_stdout)
@@ -243,6 +334,9 @@ def main():
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
         gatherer = None  # created once by_tiles is known
+
+    if args.shard == "sites":
+        return run_sites(args, saved_stdout, torch, tracs_b200, dist_mod, device, rank, world, local)
 
     w = dict(WORKLOAD)
     if args.n:

@@ -267,3 +267,20 @@ def test_synth_slabs_are_columns_of_the_whole():
         slab = torch.empty((n, pitch), dtype=torch.uint8, device="cuda")
         tracs_b200.synth_device(slab.data_ptr(), n, hi - lo, pitch, site_offset=lo, L_total=L, **kw)
         assert torch.equal(slab[:, :hi - lo], whole[:, lo:hi])
+
+
+def test_sites_driver_world1_matches_fused_path():
+    import torch
+    from tracs_b200 import sites
+    s = synth.generate(500, 150_000, p_var=0.06, n_clusters=60, mu=4, p_N=0.002, seed=81)
+    days = np.random.default_rng(4).integers(0, 150, size=500).astype(np.int32)
+    n, L = s.shape
+    pitch = (L + 127) // 128 * 128
+    buf = torch.full((n, pitch), ord("N"), dtype=torch.uint8, device="cuda")
+    buf[:, :L] = torch.from_numpy(s).cuda()
+    res, st = sites.sweep(torch, None, torch.device("cuda"), 0, 1, buf.data_ptr(), n, L, pitch, L, 20, days=days)
+    ref = tracs_b200.pairsnp_matrix(s, dist=20, days=days)
+    for k in ("rows", "cols", "dist", "ncomp"):
+        assert res[k].tolist() == ref[k].tolist()
+    assert np.array_equal(res["datediff"], ref["datediff"])
+    assert np.allclose(res["p0_log"], ref["p0_log"], rtol=1e-12) and np.allclose(res["eK"], ref["eK"], rtol=1e-12)

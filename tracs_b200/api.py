@@ -27,6 +27,12 @@ def pairsnp(fasta, n_threads, dist, filter):
 def trans_dist(snpdiff, datediff, lamb, beta, threshold_Ek):
     """TRACS.trans_dist (src/python_bindings.cpp:19-21; src/transcluster.hpp:240-287).
     Returns (log p0 list, E[K] list)."""
+    p0, eK = trans_dist_np(snpdiff, datediff, lamb, beta, threshold_Ek)
+    return p0.tolist(), eK.tolist()
+
+
+def trans_dist_np(snpdiff, datediff, lamb, beta, threshold_Ek):
+    """trans_dist returning NumPy arrays (no list conversion)."""
     snp = np.ascontiguousarray(snpdiff, dtype=np.int32)
     dt = np.ascontiguousarray(datediff, dtype=np.float64)
     if snp.shape != dt.shape:
@@ -37,7 +43,7 @@ def trans_dist(snpdiff, datediff, lamb, beta, threshold_Ek):
     eK = np.empty(n, np.float64)
     _lib.check(_lib.lib().tracs_trans_dist(snp.ctypes.data, dt.ctypes.data, n, float(lamb), float(beta), float(threshold_Ek),
                                           p0.ctypes.data, eK.ctypes.data))
-    return p0.tolist(), eK.tolist()
+    return p0, eK
 
 
 def lprob_k_given_N(N, k, delta, lamb, beta, lgamma):

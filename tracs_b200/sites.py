@@ -23,6 +23,9 @@ def slab_bounds(L_total, rank, world, align=128):
     return lo, hi
 
 
+_OUT = None  # cached page-locked result block (rank 0)
+
+
 class _Dev:
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
@@ -71,17 +74,47 @@ def sweep(torch, dist_mod, device, rank, world, slab_ptr, n, L_slab, pitch, L_to
         stats["n_candidates_all"] = E
         if rank != 0:
             return None, stats
+        # rank 0: threshold, compared sites and the transmission table stay on the device; ONE copy of the
+        # finished columns into cached page-locked memory
         keep = (d[:E] <= dist) if E else torch.zeros(0, dtype=torch.bool, device=device)
-        k = keys[:E][keep].cpu().numpy().astype(np.uint64)
-        res = {"rows": k >> np.uint64(32), "cols": k & np.uint64(0xFFFFFFFF),
-               "dist": d[:E][keep].cpu().numpy().astype(np.uint64),
-               "ncomp": (L_total - u[:E][keep].cpu().numpy().astype(np.int64)).astype(np.uint64),
-               "p0_log": None, "eK": None, "datediff": None}
-        if days is not None and len(k):
-            days = np.asarray(days)
-            dt = np.abs(days[res["rows"].astype(np.int64)] * 86400.0 - days[res["cols"].astype(np.int64)] * 86400.0) / 31556952.0
-            p0, eK = api.trans_dist(res["dist"].astype(np.int32), dt, lamb, beta, threshold_Ek)
-            res["p0_log"], res["eK"], res["datediff"] = np.asarray(p0), np.asarray(eK), dt
+        k = keys[:E][keep]
+        rows_t, cols_t = k >> 32, k & 0xFFFFFFFF
+        d_t = d[:E][keep].to(torch.int64)
+        nn_t = L_total - u[:E][keep].to(torch.int64)
+        cols_out = [rows_t, cols_t, d_t, nn_t]
+        names = ["rows", "cols", "dist", "ncomp"]
+        if days is not None and k.numel():
+            # day-resolution dates: the memo key of trans_dist is (d, |day_i - day_j|); evaluate each used key once
+            days_t = torch.as_tensor(np.asarray(days, dtype=np.int64), device=device)
+            dd = (days_t[rows_t] - days_t[cols_t]).abs()
+            DD = int(dd.max().item()) + 1
+            key = d_t * DD + dd
+            used = torch.nonzero(torch.bincount(key, minlength=(dist + 1) * DD)).flatten().cpu().numpy()
+            p0k, eKk = api.trans_dist_np((used // DD).astype(np.int32), (used % DD) * 86400.0 / 31556952.0, lamb, beta, threshold_Ek)
+            lut = np.zeros((2, (dist + 1) * DD))
+            lut[0, used], lut[1, used] = p0k, eKk
+            lut_t = torch.as_tensor(lut, device=device)
+            # tensor / tensor is a true IEEE division (tensor / python-scalar multiplies by the reciprocal on CUDA)
+            year = torch.full((), 31556952.0, dtype=torch.float64, device=device)
+            cols_out += [lut_t[0][key], lut_t[1][key], torch.div(dd.to(torch.float64) * 86400.0, year)]
+            names += ["p0_log", "eK", "datediff"]
+        res = {"p0_log": None, "eK": None, "datediff": None}
+        n_out = int(k.numel())
+        global _OUT
+        need = 8 * n_out * len(cols_out)
+        if _OUT is None or _OUT.numel() < need:
+            _OUT = torch.empty(int(need * 1.25) + 64, dtype=torch.uint8, pin_memory=(device.type == "cuda"))
+        off = 0
+        for nm, t in zip(names, cols_out):
+            dst = _OUT[off:off + 8 * n_out].view(t.dtype)
+            dst.copy_(t, non_blocking=True)
+            res[nm] = dst
+            off += 8 * n_out
+        if device.type == "cuda":
+            torch.cuda.current_stream(device).synchronize()
+        for nm in names:   # NumPy views of the pinned block: valid until the next sweep() call
+            a = res[nm].numpy()
+            res[nm] = a.view(np.uint64) if nm in ("rows", "cols", "dist", "ncomp") else a
         return res, stats
     finally:
         _lib.lib().tracs_site_shard_close(h)
