@@ -369,7 +369,7 @@ int tracs_pairsnp(const char *const *paths, int n_paths, int n_threads, int32_t 
     // src/pairsnp.hpp:340-343
     if (n_paths < 1 || n_paths > 2) throw std::runtime_error("Invalid number of fasta files!");
     require_device();
-    std::vector<uint8_t> ascii;
+    ByteBuf ascii;
     std::vector<std::string> names;
     uint64_t L = 0, L2 = 0;
     const uint64_t n1 = read_fasta(paths[0], n_threads, ascii, names, L);
@@ -405,12 +405,11 @@ int tracs_pairsnp(const char *const *paths, int n_paths, int n_threads, int32_t 
 int tracs_read_fasta(const char *path, int n_threads, uint8_t **seqs, size_t *n, size_t *L, char ***names) {
   *seqs = nullptr; *names = nullptr; *n = 0; *L = 0;
   return guarded([&] {
-    std::vector<uint8_t> ascii;
+    ByteBuf ascii;
     std::vector<std::string> nm;
     uint64_t len = 0;
     const uint64_t cnt = read_fasta(path, n_threads, ascii, nm, len);
-    *seqs = (uint8_t *)malloc(std::max<size_t>(1, ascii.size()));
-    if (!ascii.empty()) memcpy(*seqs, ascii.data(), ascii.size());
+    *seqs = ascii.release();
     *names = (char **)malloc(std::max<size_t>(1, nm.size()) * sizeof(char *));
     for (size_t i = 0; i < nm.size(); ++i) (*names)[i] = strdup(nm[i].c_str());
     *n = cnt;

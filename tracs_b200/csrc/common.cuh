@@ -109,6 +109,35 @@ constexpr int TILE = 128;  // samples per tile side
 constexpr int KC = 8;      // 32-site words per pipeline stage
 constexpr int STAGES = 3;  // shared-memory ring depth
 
+// Growable byte buffer for parsed sequences: realloc growth (large blocks move by mremap, no copy),
+// never zero-filled, and its storage can be handed to the caller (release()).
+struct ByteBuf {
+  uint8_t *p = nullptr;
+  size_t len = 0, cap = 0;
+  ByteBuf() {}
+  ByteBuf(const ByteBuf &) = delete;
+  ByteBuf &operator=(const ByteBuf &) = delete;
+  ~ByteBuf() { free(p); }
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    size_t c = cap ? cap + cap / 2 : (size_t)1 << 20;
+    if (c < want) c = want;
+    uint8_t *q = (uint8_t *)realloc(p, c);
+    if (!q) throw std::bad_alloc();
+    p = q;
+    cap = c;
+  }
+  uint8_t *data() { return p; }
+  size_t size() const { return len; }
+  uint8_t *release() {
+    if (!p) p = (uint8_t *)malloc(1);
+    uint8_t *q = p;
+    p = nullptr;
+    len = cap = 0;
+    return q;
+  }
+};
+
 // FASTA reader (fasta.cpp): kseq-compatible record semantics (reference src/kseq.h:170-208).
 struct Alignment {
   std::vector<uint8_t> ascii;  // n * L bytes, row-major, pitch == L
@@ -116,8 +145,7 @@ struct Alignment {
   uint64_t n = 0, L = 0;
 };
 // appends the records of `path`; returns number of records read; throws std::runtime_error
-uint64_t read_fasta(const char *path, int n_threads, std::vector<uint8_t> &ascii, std::vector<std::string> &names,
-                    uint64_t &L);
+uint64_t read_fasta(const char *path, int n_threads, ByteBuf &ascii, std::vector<std::string> &names, uint64_t &L);
 
 // Static multi-GPU partition: row-blocks of 128 samples are dealt boustrophedon
 // (0..w-1, w-1..0, ...) so every shard sweeps (nearly) the same triangle area.

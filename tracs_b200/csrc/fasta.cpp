@@ -7,8 +7,11 @@
 //   * seq    = every printable non-space byte (33..126) up to the next '>', '@' or '+' ANYWHERE;
 //   * '+'    = FASTQ: skip that line, then consume as many quality bytes as sequence bytes;
 //   * all records of one file must have equal length (src/pairsnp.hpp:94-98).
+#include <emmintrin.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -23,31 +26,37 @@ enum State { SEEK, NAME, REST_OF_HEADER, SEQ, PLUS_LINE, QUAL, QUAL_TRAIL };
 inline bool is_space(unsigned c) { return c == ' ' || (c >= 9 && c <= 13); }
 }  // namespace
 
-uint64_t read_fasta(const char *path, int /*n_threads*/, std::vector<uint8_t> &ascii, std::vector<std::string> &names,
-                    uint64_t &L_io) {
+uint64_t read_fasta(const char *path, int /*n_threads*/, ByteBuf &ascii, std::vector<std::string> &names, uint64_t &L_io) {
   gzFile f = gzopen(path, "r");
   if (!f) throw std::runtime_error("Error reading FASTA!");
+  {
+    // size the output once: a plain file cannot hold more bases than bytes; a gzip stream of
+    // nucleotides rarely inflates more than ~4.5x
+    struct stat sb;
+    if (stat(path, &sb) == 0 && sb.st_size > 0) ascii.reserve(ascii.size() + (gzdirect(f) ? (size_t)sb.st_size : (size_t)sb.st_size * 9 / 2) + 64);
+  }
   gzbuffer(f, 1 << 20);
-  std::vector<unsigned char> buf(size_t(1) << 22);
+  std::vector<unsigned char> buf((size_t(1) << 22) + 16);
   State st = SEEK;
   std::string name;
   uint64_t count = 0, L = 0;
-  size_t rec_start = ascii.size();  // where the current record's bases begin in `ascii`
+  size_t len = ascii.size();        // bytes of `ascii` in use
+  size_t rec_start = len;           // where the current record's bases begin in `ascii`
   uint64_t qual_seen = 0;
   bool name_started = false;
   bool failed_len = false, truncated = false;
 
   auto finish_record = [&]() {
-    uint64_t len = ascii.size() - rec_start;
-    if (count > 0 && len != L) failed_len = true;
-    L = len;
+    const uint64_t rec_len = len - rec_start;
+    if (count > 0 && rec_len != L) failed_len = true;
+    L = rec_len;
     names.push_back(name);
     count++;
-    rec_start = ascii.size();
+    rec_start = len;
   };
 
   for (;;) {
-    int got = gzread(f, buf.data(), (unsigned)buf.size());
+    int got = gzread(f, buf.data(), (unsigned)(buf.size() - 16));
     if (got < 0) {
       gzclose(f);
       throw std::runtime_error("Error reading FASTA!");
@@ -84,26 +93,47 @@ uint64_t read_fasta(const char *path, int /*n_threads*/, std::vector<uint8_t> &a
           }
           break;
         case SEQ: {
-          const unsigned char *q = p;
-          while (q < end) {
-            unsigned c = *q;
-            if (c == '>' || c == '@' || c == '+') break;
-            ++q;
-          }
-          // append printable bytes of [p, q)
-          size_t old = ascii.size();
-          ascii.resize(old + (q - p));
-          uint8_t *o = ascii.data() + old;
-          for (const unsigned char *r = p; r < q; ++r) {
-            unsigned c = *r;
+          // Bulk copy of sequence bytes, 16 at a time (SSE2). A byte is "special" if it ends the
+          // sequence ('>', '@', '+') or is not printable (newline, CR, space, ...): those are dropped.
+          ascii.reserve(len + (size_t)(end - p) + 16);
+          uint8_t *o = ascii.data() + len;
+          const __m128i c_gt = _mm_set1_epi8('>'), c_at = _mm_set1_epi8('@'), c_pl = _mm_set1_epi8('+');
+          const __m128i c33 = _mm_set1_epi8(33), c126 = _mm_set1_epi8(126);
+          bool ended = false;
+          unsigned endc = 0;
+          while (p < end) {
+            if (end - p >= 16) {
+              const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
+              const __m128i ok_lo = _mm_cmpeq_epi8(_mm_max_epu8(v, c33), v);    // v >= 33
+              const __m128i ok_hi = _mm_cmpeq_epi8(_mm_min_epu8(v, c126), v);   // v <= 126
+              const __m128i delim = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, c_gt), _mm_cmpeq_epi8(v, c_at)), _mm_cmpeq_epi8(v, c_pl));
+              const __m128i good = _mm_andnot_si128(delim, _mm_and_si128(ok_lo, ok_hi));
+              const unsigned bad = (~(unsigned)_mm_movemask_epi8(good)) & 0xFFFFu;
+              if (!bad) {
+                _mm_storeu_si128(reinterpret_cast<__m128i *>(o), v);
+                o += 16;
+                p += 16;
+                continue;
+              }
+              const unsigned k = (unsigned)__builtin_ctz(bad);  // bytes before the first special one
+              _mm_storeu_si128(reinterpret_cast<__m128i *>(o), v);  // over-copy, only k bytes are kept
+              o += k;
+              p += k;
+            }
+            const unsigned c = *p;
+            if (c == '>' || c == '@' || c == '+') {
+              ended = true;
+              endc = c;
+              ++p;
+              break;
+            }
             *o = (uint8_t)c;
             o += (c >= 33 && c <= 126);
+            ++p;
           }
-          ascii.resize(o - ascii.data());
-          p = q;
-          if (p < end) {
-            unsigned c = *p++;
-            if (c == '+') {
+          len = (size_t)(o - ascii.data());
+          if (ended) {
+            if (endc == '+') {
               st = PLUS_LINE;
             } else {
               finish_record();
@@ -123,7 +153,7 @@ uint64_t read_fasta(const char *path, int /*n_threads*/, std::vector<uint8_t> &a
           }
           break;
         case QUAL: {
-          uint64_t need = ascii.size() - rec_start;
+          uint64_t need = len - rec_start;
           while (p < end && qual_seen < need) {
             unsigned c = *p++;
             if (c >= 33 && c <= 127) qual_seen++;
@@ -151,10 +181,11 @@ uint64_t read_fasta(const char *path, int /*n_threads*/, std::vector<uint8_t> &a
       case REST_OF_HEADER:
       case SEQ: finish_record(); break;
       case PLUS_LINE: truncated = true; break;
-      case QUAL: truncated = (qual_seen != ascii.size() - rec_start); if (!truncated) finish_record(); break;
+      case QUAL: truncated = (qual_seen != len - rec_start); if (!truncated) finish_record(); break;
       case QUAL_TRAIL: finish_record(); break;
     }
   }
+  ascii.len = len;
   if (failed_len) throw std::runtime_error("Error reading FASTA, variable sequence lengths!");
   if (truncated) throw std::runtime_error("Error reading FASTA!");
   if (count > 0) L_io = L;
