@@ -92,3 +92,53 @@ def test_distance_cli_with_filter(tmp_path, ):
     rows = _rows(out)[1:]
     exp = oracle.pairsnp([msa], dist=40, filter=True)
     assert [int(r[6]) for r in rows] == exp[4] and [int(r[3]) for r in rows] == exp[2]
+
+
+def test_config4_min_over_references(tmp_path):
+    """BASELINE.json configs[3] in miniature: several reference MSAs over overlapping sample subsets with
+    IUPAC codes and many N's; per-MSA sweeps, then min over references per unordered name pair.
+    Checked against the CPU oracle + a plain dict group-by-min, and clustering invariance
+    (connected components of `any row <= thr` == components of `min <= thr`, tracs/cluster.py:104-129)."""
+    from oracle import oracle
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    from tracs_b200 import distance, synth
+    rng = np.random.default_rng(7)
+    all_names = ["smp%03d" % i for i in range(120)]
+    per_msa, expect, any_rows = [], {}, []
+    for r in range(4):
+        members = np.sort(rng.choice(120, size=int(rng.integers(70, 120)), replace=False))
+        L = int(rng.integers(20_000, 30_000))
+        s = synth.generate(len(members), L, p_var=0.02, n_clusters=6, mu=4, p_N=0.3, p_amb=0.05, seed=40 + r, three_base=True)
+        names = [all_names[m] for m in members]
+        p = str(tmp_path / ("ref%d_combined.fasta.gz" % r))
+        synth.write_fasta(p, s, names=names)
+        got = tracs_b200.pairsnp(fasta=[p], n_threads=1, dist=100, filter=False)
+        exp = oracle.pairsnp([p], dist=100)
+        assert got[0] == exp[0] and got[1] == exp[1] and got[2] == exp[2] and got[5] == exp[5] and got[3] == names
+        per_msa.append((got[3], got[0], got[1], got[2]))
+        for i, j, d in zip(exp[0], exp[1], exp[2]):
+            a, b = names[i], names[j]
+            key = (a, b) if all_names.index(a) < all_names.index(b) else (b, a)
+            expect[key] = min(expect.get(key, 1e300), d)
+            any_rows.append((key, d))
+    A, B, V = distance.min_over_references(per_msa)
+    got_map = {}
+    for a, b, v in zip(A, B, V):
+        key = (a, b) if all_names.index(a) < all_names.index(b) else (b, a)
+        assert key not in got_map
+        got_map[key] = v
+    assert got_map == {k: float(v) for k, v in expect.items()}
+    # clustering is invariant under the combine
+    idx = {nm: k for k, nm in enumerate(all_names)}
+    for thr in (5, 20):
+        def comps(pairs):
+            if not pairs:
+                return np.arange(120)
+            r_ = [idx[a] for a, _ in pairs]
+            c_ = [idx[b] for _, b in pairs]
+            g = csr_matrix((np.ones(len(r_)), (r_, c_)), shape=(120, 120))
+            return connected_components(g, directed=False)[1]
+        c_any = comps([k for k, d in any_rows if d <= thr])
+        c_min = comps([k for k, v in got_map.items() if v <= thr])
+        assert np.array_equal(c_any, c_min)

@@ -109,3 +109,25 @@ def test_c1_shape_dense_and_thresholded():
             assert d == int(dense["dist"][e]) and nn == int(dense["ncomp"][e])
     finally:
         aln.free()
+
+
+def test_c5_shape_dense_variation():
+    # BASELINE.json configs[4] shape scaled down: EVERY site variable, unambiguous bases, no N
+    n, L = 4000, 500_000
+    aln = DevAln(n, L, seed=5, p_var=1.0, n_clusters=40, mu=5.0, p_N=0.0, p_amb=0.0, gc=0.5, gaps=0)
+    try:
+        res = tracs_b200.pairsnp_device(aln.p.value, n, L, aln.pitch, dist=20)
+        st = tracs_b200.last_stats()
+        assert st["n_variable_sites"] > 0.99 * L and st["ms_refine"] > 0
+        full = tracs_b200.pairsnp_device(aln.p.value, n, L, aln.pitch, dist=20, full_sweep=True)
+        for k in ("rows", "cols", "dist", "ncomp"):
+            assert np.array_equal(res[k], full[k])
+        assert np.all(res["ncomp"] == L)
+        rng = np.random.default_rng(5)
+        E = len(res["rows"])
+        assert E > 1000
+        for e in rng.choice(E, size=10, replace=False):
+            d, nn = _pair_truth(aln.row(int(res["rows"][e])), aln.row(int(res["cols"][e])))
+            assert d == int(res["dist"][e]) and nn == L
+    finally:
+        aln.free()

@@ -83,3 +83,29 @@ def main(argv=None):
 
 if __name__ == "__main__":
     main()
+
+
+def min_over_references(per_msa, column="dist"):
+    """Min-over-references combine. The reference only realises it implicitly: one CSV row
+    per (pair, MSA) (tracs/distance.py:159-258) and tracs/cluster.py:104-113 links a pair if ANY row is
+    under the threshold, i.e. min over MSAs <= threshold.
+
+    per_msa: iterable of (names, rows, cols, values) per reference MSA (indices into that MSA's names).
+    Returns (nameA, nameB, value) lists: one entry per unordered sample-name pair, value = min over the
+    MSAs that contain the pair, sorted by the order names were first seen. Runs on the GPU
+    (tracs_min_over_refs: radix sort + reduce-by-key)."""
+    ids = {}
+    a_all, b_all, v_all = [], [], []
+    for names, rows, cols, values in per_msa:
+        gid = np.array([ids.setdefault(nm, len(ids)) for nm in names], dtype=np.uint64)
+        if len(rows):
+            a_all.append(gid[np.asarray(rows, dtype=np.int64)])
+            b_all.append(gid[np.asarray(cols, dtype=np.int64)])
+            v_all.append(np.asarray(values, dtype=np.float64))
+    if not a_all:
+        return [], [], []
+    oa, ob, ov = api.min_over_refs(np.concatenate(a_all), np.concatenate(b_all), np.concatenate(v_all))
+    inv = [None] * len(ids)
+    for nm, k in ids.items():
+        inv[k] = nm
+    return [inv[int(x)] for x in oa], [inv[int(x)] for x in ob], ov.tolist()
