@@ -147,48 +147,63 @@ def run_reference(args, saved_stdout):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class Clocks:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle-reason sampler for the timed region. In-process NVML (nvidia_ml_py) polled from a
+    thread: spawning `nvidia-smi -lms` inside a 250 ms timed region costs more than the region itself
+    (its start-up holds driver locks and showed up as 50-200 ms stalls of single steps). The sampler is
+    initialised before warm-up; only samples taken between mark() and stop() are reported."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.rows = []
-        self.proc = None
-        self.index = index
+    def __init__(self, index, period_s=0.02):
+        self.index, self.period = index, period_s
+        self.rows, self.t_mark = [], None
+        self.ok, self.stop_flag = False, False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as ex:
+            self.err = repr(ex)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        if not self.ok:
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nm)
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.perf_counter(), sm, rs, pw))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(self.period)
+
+    def stop(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        rows = [r for r in self.rows if self.t_mark is None or r[0] >= self.t_mark]
+        if not rows:
+            rows = self.rows[-1:]
+        reasons = sorted({nm for nm, bit in self.REASONS.items() for r in rows if r[2] & bit})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(rows), "power_w_max": max([r[3] for r in rows]) if rows else None, "source": "nvml, 20 ms period"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,14 +255,15 @@ def run_sites(args, saved_stdout, torch, tracs_b200, dist_mod, device, rank, wor
             dist_mod.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync()
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step()
+    sync()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
+    clocks.mark()
     ev0.record()
     for _ in range(args.steps):
         res, st = step()
@@ -379,16 +395,17 @@ def main():
             dist_mod.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    if world > 1:
-        gatherer.drain()
-    sync()
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        res, st, merged = step()   # held like in the timed loop, so the result-buffer cache reaches its steady state
+    if world > 1:
+        gatherer.drain()
+    sync()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
+    clocks.mark()
     t_wall0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
@@ -433,7 +450,7 @@ def main():
         except Exception:
             hbm, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
         traffic = {}
-        prof = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+        prof = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof))
@@ -443,7 +460,8 @@ def main():
         def sweep_roof(wordpairs, ms, what):
             return {"bound": "int_pipe", "kernel": "k_sweep", "what": what, "achieved": wordpairs * 6 / (ms * 1e-3) / 1e9,
                     "peak": peak_wp * 6 / 1e9, "unit": "Ginstr/s", "frac": (wordpairs * 6 / (ms * 1e-3)) / (peak_wp * 6),
-                    "traffic": traffic.get("dram_bytes_per_launch") if what.startswith("full") else None,
+                    "traffic": traffic.get("k_sweep_full_length_dram_bytes_per_launch") if what.startswith("full") else
+                    traffic.get("k_sweep_prefilter_dram_bytes_per_launch"),
                     "achieved_wordpairs_per_s": wordpairs / (ms * 1e-3), "ms_per_launch": ms,
                     "peak_source": "measured in this run (tracs_int_peak: register-resident LOP3 and POPC loops; a word-pair needs "
                                    "4 LOP3 on the 64-lane ALU pipe and 1 POPC on the 16-lane XU pipe => min(lop3/4, popc) word-pairs/s)",
@@ -453,20 +471,30 @@ def main():
         npitch_words = max(32, ((L + 31) // 32 + 31) // 32 * 32)
         pack_bytes = n * L + n * npitch_words * 4 + n * (npitch_words // 32)
         roof_pack = {"bound": "hbm", "kernel": "k_pack", "achieved": pack_bytes / (avg("ms_pack") * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                     "frac": pack_bytes / (avg("ms_pack") * 1e-3) / 1e9 / hbm, "traffic": traffic.get("pack_dram_bytes_per_launch"),
+                     "frac": pack_bytes / (avg("ms_pack") * 1e-3) / 1e9 / hbm, "traffic": traffic.get("k_pack_dram_bytes_per_launch"),
                      "ms_per_launch": avg("ms_pack"), "algorithmic_bytes": pack_bytes, "peak_source": hbm_src}
         prefiltered = avg("n_candidates") > 0 or avg("ms_refine") > 0
         roof_sweep = sweep_roof(avg("swept_wordpairs"), avg("ms_sweep"),
                                 "prefilter launch (first 64 words of every pair)" if prefiltered else "full-length sweep")
         # the same tile kernel forced over the full length (what an unthresholded / dense run executes)
-        res_full = tracs_b200.pairsnp_device(seqs.data_ptr(), n, L, pitch, full_sweep=True, **kw)
+        t_full = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res_full = tracs_b200.pairsnp_device(seqs.data_ptr(), n, L, pitch, full_sweep=True, copy=False, **kw)
+            torch.cuda.synchronize()
+            t_full.append(time.perf_counter() - t0)
         st_full = tracs_b200.last_stats()
         roof_full = sweep_roof(st_full["swept_wordpairs"], st_full["ms_sweep"], "full-length sweep (prefilter disabled)")
+        roof_full["whole_step_ms"] = 1e3 * min(t_full)
+        roof_full["whole_step_value"] = n_msa * P * L / min(t_full)
         roof_full["edges_equal_default_path"] = bool(np.array_equal(res_full["rows"], res["rows"]) and np.array_equal(res_full["cols"], res["cols"])
                                                      and np.array_equal(res_full["dist"], res["dist"]))
         roof = roof_pack if avg("ms_pack") >= avg("ms_sweep") else roof_sweep
         stages = {k: avg(k) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_d2h", "ms_total")}
         stages["n_candidates"] = avg("n_candidates")
+        stages["per_step_ms_total"] = [round(s_["ms_total"], 2) for s_ in stats]
+        stages["per_step_ms_d2h"] = [round(s_["ms_d2h"], 2) for s_ in stats]
         line = {
             "metric": "site-pair comparisons/s (P*L/t)", "value": value, "unit": "site-pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if by_tiles else "weak", "vs_baseline": None,
@@ -476,6 +504,8 @@ def main():
                        "msas": n_msa,
                        "parallelism": ("triangle row-blocks of one MSA dealt boustrophedon over %d GPUs; ingest replicated" % world) if by_tiles
                        else ("%d independent MSA(s), one per GPU (tracs/distance.py:159 loop); edge lists gathered to rank 0" % world),
+                       "algorithm": "exact filter-and-refine: tile sweep over the first 64 words of every pair, per-pair refinement of the "
+                                    "survivors; roofline_kernels.k_sweep_full_length gives the same step with the full-length tile sweep",
                        "l2": "inputs (%.1f GB ASCII) larger than L2; no flush needed" % (n * pitch / 1e9)},
             "clocks": clk, "gpu_launches": launches, "roofline": roof,
             "roofline_kernels": {"k_pack": roof_pack, "k_sweep": roof_sweep, "k_sweep_full_length": roof_full}, "stages_ms": stages,

@@ -160,8 +160,8 @@ int tracs_site_shard_close(void *handle);
 const char *tracs_last_error(void);
 int tracs_last_stats(tracs_stats_t *out);
 int tracs_device_count(void);
-/* Scratch buffers are cached in the device's default memory pool between calls; this returns them
- * to the driver. */
+/* Device scratch blocks and page-locked result blocks are cached by the library between calls
+ * (reused whole, by size); this returns the idle ones to the driver. */
 int tracs_trim(void);
 int tracs_set_device(int device);
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <functional>
 #include <numeric>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>
@@ -18,17 +19,64 @@ thread_local std::string g_err;
 thread_local tracs_stats_t g_stats;
 void set_error(const std::string &msg) { g_err = msg; }
 
-void pool_init() {
-  static thread_local int done_for = -1;
+// ---- device block cache ------------------------------------------------------------------------------
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::unordered_map<void *, std::pair<size_t, int>> live;  // block -> (size, device)
+  std::multimap<size_t, std::pair<void *, int>> idle;       // size -> (block, device)
+};
+DevCache &dev_cache() {
+  static DevCache *dc = new DevCache();  // leaked on purpose (outlives CUDA teardown)
+  return *dc;
+}
+constexpr size_t DEV_GRANULE = 1 << 16;
+}  // namespace
+
+void *dev_cache_alloc(size_t bytes) {
+  const size_t want = (bytes + DEV_GRANULE - 1) / DEV_GRANULE * DEV_GRANULE;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return;
-  if (done_for == dev) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  TRACS_CK(cudaGetDevice(&dev));
+  DevCache &dc = dev_cache();
+  {
+    std::lock_guard<std::mutex> g(dc.mu);
+    // smallest idle block on this device that fits without wasting more than a quarter of it
+    for (auto it = dc.idle.lower_bound(want); it != dc.idle.end() && it->first <= want + want / 4 + DEV_GRANULE; ++it) {
+      if (it->second.second != dev) continue;
+      void *p = it->second.first;
+      dc.live[p] = {it->first, dev};
+      dc.idle.erase(it);
+      return p;
+    }
   }
-  done_for = dev;
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e == cudaErrorMemoryAllocation) {  // make room: drop every idle block of this device and retry once
+    cudaGetLastError();
+    std::vector<void *> drop;
+    {
+      std::lock_guard<std::mutex> g(dc.mu);
+      for (auto it = dc.idle.begin(); it != dc.idle.end();) {
+        if (it->second.second == dev) { drop.push_back(it->second.first); it = dc.idle.erase(it); } else ++it;
+      }
+    }
+    for (void *q : drop) cudaFree(q);
+    e = cudaMalloc(&p, want);
+  }
+  TRACS_CK(e);
+  std::lock_guard<std::mutex> g(dc.mu);
+  dc.live[p] = {want, dev};
+  return p;
+}
+
+void dev_cache_free(void *p) {
+  if (!p) return;
+  DevCache &dc = dev_cache();
+  std::lock_guard<std::mutex> g(dc.mu);
+  auto it = dc.live.find(p);
+  if (it == dc.live.end()) return;
+  dc.idle.emplace(it->second.first, std::make_pair(p, it->second.second));
+  dc.live.erase(it);
 }
 
 // ---- page-locked host block cache ----------------------------------------------------------------
@@ -587,12 +635,13 @@ int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev
 
 int tracs_trim(void) {
   return guarded([&] {
-    int dev = 0;
-    TRACS_CK(cudaGetDevice(&dev));
-    cudaMemPool_t pool;
-    TRACS_CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     TRACS_CK(cudaDeviceSynchronize());
-    TRACS_CK(cudaMemPoolTrimTo(pool, 0));
+    {
+      DevCache &dc = dev_cache();
+      std::lock_guard<std::mutex> g(dc.mu);
+      for (auto &kv : dc.idle) cudaFree(kv.second.first);
+      dc.idle.clear();
+    }
     HostPool &hp = host_pool();
     std::lock_guard<std::mutex> g(hp.mu);
     for (auto &kv : hp.idle)

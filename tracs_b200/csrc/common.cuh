@@ -32,9 +32,12 @@ struct CudaError {
     }                                                                                              \
   } while (0)
 
-// Keeps freed blocks in the default memory pool instead of returning them to the driver, so the
-// multi-GB scratch buffers of one call are reused by the next (tracs_trim() releases them).
-void pool_init();
+// Device scratch comes from a block cache owned by the library: a freed block is kept whole and
+// handed to the next request of (about) the same size, so the multi-GB buffers of one call are reused
+// by the next one without fragmentation or driver calls (tracs_trim() releases the idle blocks).
+// All work of a call is issued on one stream, so reuse is ordered by the stream.
+void *dev_cache_alloc(size_t bytes);
+void dev_cache_free(void *p);
 
 void require_device();  // throws unless a CUDA device is usable (there is no CPU fallback)
 
@@ -66,17 +69,13 @@ struct DevBuf {
   explicit DevBuf(size_t count) { alloc(count); }
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  // stream-ordered allocation from the device's default pool (kept across calls: see pool_init)
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) {
-      pool_init();
-      TRACS_CK(cudaMallocAsync((void **)&p, count * sizeof(T), (cudaStream_t)0));
-    }
+    if (count) p = (T *)dev_cache_alloc(count * sizeof(T));
   }
   void release() {
-    if (p) cudaFreeAsync(p, (cudaStream_t)0);
+    if (p) dev_cache_free(p);
     p = nullptr;
     n = 0;
   }
