@@ -490,6 +490,31 @@ def main():
         roof_full["whole_step_value"] = n_msa * P * L / min(t_full)
         roof_full["edges_equal_default_path"] = bool(np.array_equal(res_full["rows"], res["rows"]) and np.array_equal(res_full["cols"], res["cols"])
                                                      and np.array_equal(res_full["dist"], res["dist"]))
+        # the same full-length sweep on the tensor cores (tcgen05 kind::i8 one-hot GEMM, K = 5 int8 per site)
+        roof_tc = None
+        try:
+            t_tc = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                res_tc = tracs_b200.pairsnp_device(seqs.data_ptr(), n, L, pitch, full_sweep="tc", copy=False, **kw)
+                torch.cuda.synchronize()
+                t_tc.append(time.perf_counter() - t0)
+            st_tc = tracs_b200.last_stats()
+            macs = st_tc["n_tiles"] * 128 * 128 * st_tc["n_words"] * 32 * 5   # executed: 5 int8 columns per site, whole tiles
+            alg_macs = st_tc["n_pairs"] * ((st_tc["n_variable_sites"] + 31) // 32) * 32 * 4   # P * 4 * V_eff
+            roof_tc = {"bound": "tensor", "kernel": "k_sweep_tc", "what": "full-length sweep, tcgen05.mma kind::i8 M128 N128 K32, operands expanded "
+                       "from the bit-planes in shared memory, int32 accumulators in TMEM",
+                       "achieved": 2 * alg_macs / (st_tc["ms_sweep"] * 1e-3) / 1e12, "peak": 4500.0, "unit": "TOP/s",
+                       "frac": 2 * alg_macs / (st_tc["ms_sweep"] * 1e-3) / 1e12 / 4500.0,
+                       "peak_source": "NOMINAL dense int8 (4.5 POP/s); no measured int8 figure in MEASURED_PEAKS.json",
+                       "executed_tops": 2 * macs / (st_tc["ms_sweep"] * 1e-3) / 1e12, "traffic": None,
+                       "ms_per_launch": st_tc["ms_sweep"], "whole_step_ms": 1e3 * min(t_tc),
+                       "speedup_vs_int_pipe_kernel": st_full["ms_sweep"] / st_tc["ms_sweep"],
+                       "edges_equal_default_path": bool(np.array_equal(res_tc["rows"], res["rows"]) and np.array_equal(res_tc["cols"], res["cols"])
+                                                        and np.array_equal(res_tc["dist"], res["dist"]))}
+        except Exception as ex:
+            roof_tc = {"kernel": "k_sweep_tc", "error": repr(ex)}
         roof = roof_pack if avg("ms_pack") >= avg("ms_sweep") else roof_sweep
         stages = {k: avg(k) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_d2h", "ms_total")}
         stages["n_candidates"] = avg("n_candidates")
@@ -508,7 +533,8 @@ def main():
                                     "survivors; roofline_kernels.k_sweep_full_length gives the same step with the full-length tile sweep",
                        "l2": "inputs (%.1f GB ASCII) larger than L2; no flush needed" % (n * pitch / 1e9)},
             "clocks": clk, "gpu_launches": launches, "roofline": roof,
-            "roofline_kernels": {"k_pack": roof_pack, "k_sweep": roof_sweep, "k_sweep_full_length": roof_full}, "stages_ms": stages,
+            "roofline_kernels": {"k_pack": roof_pack, "k_sweep": roof_sweep, "k_sweep_full_length": roof_full, "k_sweep_tc_full_length": roof_tc},
+            "stages_ms": stages,
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
         }
 

@@ -87,7 +87,9 @@ typedef struct tracs_opts {
   int32_t want_trans;  /* fused transmission likelihood: needs days != NULL                      */
   const int32_t *days; /* host: sampling day number per sample (days since any epoch)            */
   double lamb, beta, threshold_Ek; /* trans_dist args (src/transcluster.hpp:241)                 */
-  int32_t sweep_variant; /* 0 = prefilter + refine when the threshold allows; 1 = always full tile sweep */
+  int32_t sweep_variant; /* 0 = prefilter + refine when the threshold allows; 1 = always the full-length LOP3/POPC
+                          * tile sweep; 2 = full-length sweep on the tensor cores (tcgen05 int8 one-hot GEMM; needs
+                          * single-base-or-N masks at the variable sites, else the call fails) */
   int32_t keep_on_device; /* also return the edge columns packed in device memory (tracs_edges_t.dev_packed) */
 } tracs_opts_t;
 

@@ -284,3 +284,39 @@ def test_sites_driver_world1_matches_fused_path():
         assert res[k].tolist() == ref[k].tolist()
     assert np.array_equal(res["datediff"], ref["datediff"])
     assert np.allclose(res["p0_log"], ref["p0_log"], rtol=1e-12) and np.allclose(res["eK"], ref["eK"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,L,dist", [(100, 3000, IMAX), (300, 20000, 30), (129, 40000, 2000), (513, 9000, IMAX)])
+def test_tensor_core_sweep_matches_oracle(oracle_mod, n, L, dist):
+    # K1': tcgen05 int8 one-hot GEMM with the N-column correction; single bases, N, gaps, lower case -- no 2-/3-base codes
+    s = synth.generate(n, L, p_var=0.08, n_clusters=5, mu=4, p_N=0.05, p_amb=0.0, seed=n + L, lowercase=0.05, odd_chars=0.01)
+    res = tracs_b200.pairsnp_matrix(s, dist=dist, full_sweep="tc")
+    _cmp(res, oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4))
+    st = tracs_b200.last_stats()
+    assert st["ms_refine"] == 0 and st["n_candidates"] == 0
+
+
+def test_tensor_core_sweep_refuses_partial_ambiguity():
+    s = synth.generate(64, 2000, p_var=0.1, n_clusters=3, mu=3, p_N=0.01, p_amb=0.2, seed=9)
+    with pytest.raises(RuntimeError, match="IUPAC"):
+        tracs_b200.pairsnp_matrix(s, dist=50, full_sweep="tc")
+    tracs_b200.pairsnp_matrix(s, dist=50)  # the LOP3/POPC path takes it
+
+
+def test_tensor_core_sweep_modes(oracle_mod):
+    # query x db ranges, row-block shards and the automatic choice (unthresholded => full-length => tensor cores)
+    s = synth.generate(700, 6000, p_var=0.08, n_clusters=6, mu=4, p_N=0.03, seed=91)
+    for n1 in (100, 300):
+        res = tracs_b200.pairsnp_matrix(s, dist=200, i_end=n1, j_start=n1, full_sweep="tc")
+        _cmp(res, oracle_mod.pairsnp_ascii(s, i_end=n1, j_start=n1, dist=200, n_threads=4))
+    full = tracs_b200.pairsnp_matrix(s, dist=IMAX)            # auto: no prefilter possible -> k_sweep_tc
+    _cmp(full, oracle_mod.pairsnp_ascii(s, dist=IMAX, n_threads=4))
+    pop = tracs_b200.pairsnp_matrix(s, dist=IMAX, full_sweep=True)   # forced LOP3/POPC kernel
+    for k in ("rows", "cols", "dist", "ncomp"):
+        assert pop[k].tolist() == full[k].tolist()
+    parts = [tracs_b200.pairsnp_matrix(s, dist=150, shard_rank=r, shard_world=3, full_sweep="tc") for r in range(3)]
+    one = tracs_b200.pairsnp_matrix(s, dist=150, full_sweep=True)
+    key = np.concatenate([(p["rows"] << np.uint64(32)) | p["cols"] for p in parts])
+    order = np.argsort(key, kind="stable")
+    for k in ("rows", "cols", "dist", "ncomp"):
+        assert np.concatenate([p[k] for p in parts])[order].tolist() == one[k].tolist()

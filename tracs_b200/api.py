@@ -79,7 +79,7 @@ def make_opts(dist=INT32_MAX, i_end=0, j_start=0, shard_rank=0, shard_world=1, w
     o.shard_rank = int(shard_rank)
     o.shard_world = int(shard_world)
     o.want_ncomp = int(bool(want_ncomp))
-    o.sweep_variant = 1 if full_sweep else 0
+    o.sweep_variant = 2 if full_sweep == "tc" else (1 if full_sweep else 0)
     o.keep_on_device = int(bool(keep_on_device))
     keep = None
     if days is not None:

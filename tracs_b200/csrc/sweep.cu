@@ -205,7 +205,8 @@ __global__ void k_siteflags(const uint32_t *__restrict__ colmask, uint64_t L, ui
 // K0b: bit-slice the variable sites. One warp per (word, sample-chunk); lane <-> site.
 __global__ void __launch_bounds__(256)
 k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uint32_t *__restrict__ site_idx, uint64_t V,
-         uint4 *__restrict__ planes, uint64_t Npad, uint4 *__restrict__ planesT, uint64_t Wp, uint32_t schunk) {
+         uint4 *__restrict__ planes, uint64_t Npad, uint4 *__restrict__ planesT, uint64_t Wp, uint32_t schunk,
+         uint32_t *__restrict__ amb_flag) {
   __shared__ uint8_t lut[256];
   lut[threadIdx.x] = (uint8_t)base_mask(threadIdx.x);
   __syncthreads();
@@ -226,6 +227,8 @@ k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uin
       const uint64_t s = sb + t;
       if (s >= s1) break;
       const uint32_t m = live ? lut[ch[t]] : 15u;
+      // two- or three-base codes at a variable site rule out the one-hot GEMM identity (sweep_tc.inl)
+      if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) *amb_flag = 1u;
       const uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
       const uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
       const uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
@@ -681,6 +684,10 @@ __global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t
   dt[e] = ((double)dd * 86400.0) / 31556952.0;
 }
 
+}  // namespace tracs
+#include "sweep_tc.inl"
+namespace tracs {
+
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
@@ -695,6 +702,7 @@ struct Ingested {
   DevBuf<uint32_t> nplane, ncount, site_idx;
   DevBuf<uint8_t> nsum;
   DevBuf<uint4> planes, planesT;
+  bool partial_ambiguity = false;      // some variable site carries a 2- or 3-base IUPAC code
 };
 
 // ASCII matrix (device) -> N-plane + summaries + variable-site bit-planes (K0a + K0b)
@@ -773,9 +781,15 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   if (W > 0) {
     const uint32_t schunk = 512;
     dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
-    k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, g.planes.p, Npad, g.planesT.p, Wp, schunk);
+    DevBuf<uint32_t> amb(1);
+    TRACS_CK(cudaMemsetAsync(amb.p, 0, 4, st));
+    k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, g.planes.p, Npad, g.planesT.p, Wp, schunk, amb.p);
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
+    uint32_t h_amb = 0;
+    TRACS_CK(cudaMemcpyAsync(&h_amb, amb.p, 4, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaStreamSynchronize(st));
+    g.partial_ambiguity = h_amb != 0;
   }
   S.ms_compact += T.stop();
   if (!keep_site_idx) site_idx.release();
@@ -951,7 +965,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     // those per pair (k_refine); otherwise fall back to the full-length tile sweep.
     unsigned long long E = 0;
     bool refined = false;
-    const bool try_prefilter = o.sweep_variant != 1 && o.dist >= 0 && (uint64_t)o.dist < (uint64_t)PREFILTER_WORDS * 32 &&
+    const bool try_prefilter = o.sweep_variant == 0 && o.dist >= 0 && (uint64_t)o.dist < (uint64_t)PREFILTER_WORDS * 32 &&
                                Wp >= 4 * PREFILTER_WORDS;
     if (try_prefilter) {
       a.Wp = PREFILTER_WORDS;
@@ -985,7 +999,20 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     if (!refined) {
       a.Wp = Wp;
       a.keys = keys.p; a.dvals = dv.p;
+      // full-length sweep: the tensor-core kernel (1.4x the LOP3/POPC kernel at C2, profiles/r1_tc_ncu.md) whenever
+      // the masks allow its identity; variant 1 forces the LOP3/POPC kernel, variant 2 insists on tensor cores
+      const bool use_tc = o.sweep_variant == 2 || (o.sweep_variant == 0 && !ing.partial_ambiguity && Wp >= 64);
+      if (o.sweep_variant == 2 && ing.partial_ambiguity)
+        throw std::runtime_error("tensor-core sweep requested but the alignment has 2-/3-base IUPAC codes at variable sites");
       T.start();
+      if (use_tc) {
+        static bool tc_attr = false;
+        if (!tc_attr) {
+          TRACS_CK(cudaFuncSetAttribute(k_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+          tc_attr = true;
+        }
+        k_sweep_tc<<<(unsigned)std::min<uint64_t>(n_tiles, (uint64_t)n_sm), TC_THREADS, TC_SMEM, st>>>(a);
+      } else
       k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
       S.kernel_launches++;
       TRACS_CK(cudaGetLastError());
