@@ -23,7 +23,7 @@ constexpr int TC_KCH = TC_PLANES * 2;                      // 16-byte K chunks p
 constexpr uint32_t TC_SIDE_BYTES = TC_KCH * (TILE / 8) * 128;   // 20480: one operand, one word
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_SIDE_BYTES;
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024;
-constexpr int TC_PRODUCERS = 256;   // 8 warps: (operand side, row); 16 warps measured no faster
+constexpr int TC_PRODUCERS = 256;   // 8 warps: thread = (operand side, row)
 constexpr int TC_THREADS = TC_PRODUCERS + 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(const SweepArgs a) {
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&full[s], TC_PRODUCERS);
+      mbar_init(&full[s], TC_PRODUCERS / 32);  // one arrival per producer warp
       mbar_init(&empty[s], 1);
     }
     mbar_init(&tmem_full, 1);
@@ -80,12 +80,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(const SweepArgs a) {
       const uint4 *src = a.planes + (size_t)(side ? cb : rb) * TILE + r;
       const uint32_t row_off = (r >> 3) * 128 + (r & 7) * 16;
       const uint32_t nmul = side ? 1u : 0xFDu;  // N column: -3 on the row operand, +1 on the column operand
-      uint4 nxt = __ldg(src);
-      for (uint32_t w = 0; w < nw; ++w, ++it) {
-        const uint4 x = nxt;
-        if (w + 1 < nw) nxt = __ldg(src + (size_t)(w + 1) * a.Npad);
-        const uint32_t slot = it % TC_STAGES;
-        mbar_wait(&empty[slot], ((it / TC_STAGES) & 1u) ^ 1u);
+      // Two words per trip: both stages are written, then ONE proxy fence and two arrivals, so the
+      // store -> fence -> arrive latency chain is paid once per pair of words (the producers were
+      // latency-bound on it, not ALU- or store-bound: profiles/r1_tc_ncu.md). Wp is a multiple of 8.
+      auto expand = [&](const uint4 &x, uint32_t slot) {
         uint8_t *dst = stage_base + (size_t)slot * TC_STAGE_BYTES + side * TC_SIDE_BYTES + row_off;
         const uint32_t pl[TC_PLANES] = {x.x, x.y, x.z, x.w, x.x & x.y & x.z & x.w};
 #pragma unroll
@@ -102,8 +100,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(const SweepArgs a) {
             *reinterpret_cast<uint4 *>(dst + (size_t)(2 * p + h) * ((TILE / 8) * 128)) = o;
           }
         }
+      };
+      // A pipeline step is a PAIR of words (two 40 KB stages): one "empty" wait, one proxy fence and one
+      // "full" arrival per pair, and the MMA side commits once per pair. Probes (tools/tc_rate.cu and
+      // handshake-only runs of this kernel) show that MMAs queued behind a tcgen05.commit start only
+      // after it retires: ~370 clk of drained pipe per commit, against 64 clk per MMA. Per-word commits
+      // cost 690 clk/word, per-pair commits 505 (the MMAs alone: 320); shared memory holds 4 words.
+      uint4 c0 = __ldg(src), c1 = __ldg(src + (size_t)a.Npad);
+      for (uint32_t w = 0; w < nw; w += 2, it += 2) {
+        const uint4 x0 = c0, x1 = c1;
+        if (w + 2 < nw) {
+          c0 = __ldg(src + (size_t)(w + 2) * a.Npad);
+          c1 = __ldg(src + (size_t)(w + 3) * a.Npad);
+        }
+        const uint32_t pair = (it >> 1) % (TC_STAGES / 2);
+        mbar_wait(&empty[pair], (((it >> 1) / (TC_STAGES / 2)) & 1u) ^ 1u);
+        expand(x0, 2 * pair);
+        expand(x1, 2 * pair + 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
-        mbar_arrive(&full[slot]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[pair]);  // 8 arrivals per stage instead of 256 on one shared-memory word
       }
     } else {
       // ===== MMA issuer: one elected thread =====
@@ -113,24 +129,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(const SweepArgs a) {
         const uint32_t k_stride = (TILE / 8) * 128, m_stride = 128;
         mbar_wait(&tmem_empty, (tile_iter & 1u) ^ 1u);  // epilogue of the previous tile has drained TMEM
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (uint32_t w = 0; w < nw; ++w, ++it) {
-          const uint32_t slot = it % TC_STAGES;
-          mbar_wait(&full[slot], (it / TC_STAGES) & 1u);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_u32(stage_base + (size_t)slot * TC_STAGE_BYTES), sb = sa + TC_SIDE_BYTES;
+        // The issuing thread is ONE thread running dependent scalar code between MMAs (each MMA occupies the
+        // tensor pipe for only 64 clk), so everything that can be folded at compile time is: the loop is
+        // unrolled over the two pair-stages, descriptors are a base plus immediate offsets.
+        const uint64_t desc0 = umma_desc(smem_u32(stage_base), k_stride, m_stride);
+        for (uint32_t w = 0; w < nw; w += 4, it += 4) {
+          const uint32_t phase = ((it >> 1) / (TC_STAGES / 2)) & 1u;
 #pragma unroll
-          for (int p = 0; p < TC_PLANES; ++p) {
-            const uint64_t da = umma_desc(sa + p * 2 * k_stride, k_stride, m_stride);
-            const uint64_t db = umma_desc(sb + p * 2 * k_stride, k_stride, m_stride);
-            const uint32_t acc = (w | (uint32_t)p) != 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem),
-                "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
-                : "memory");
+          for (int pair = 0; pair < TC_STAGES / 2; ++pair) {
+            mbar_wait(&full[pair], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+              for (int p = 0; p < TC_PLANES; ++p) {
+                const uint64_t da = desc0 + (uint64_t)(((2 * pair + q) * TC_STAGE_BYTES + p * 2 * k_stride) >> 4);
+                const uint64_t db = da + (uint64_t)(TC_SIDE_BYTES >> 4);
+                const uint32_t acc = (pair | q | p) != 0 ? 1u : (uint32_t)(w != 0u);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem),
+                    "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
+                    : "memory");
+              }
+            }
+            // commit: both stages of the pair may be overwritten once these MMAs have read them
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&empty[pair])) : "memory");
           }
-          // commit: the stage may be overwritten once these MMAs have read it
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&empty[slot])) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&tmem_full)) : "memory");
       } else {
