@@ -73,6 +73,7 @@ typedef struct tracs_stats {
   float ms_total;            /* device time of the whole call (events on the call's stream) */
   float ms_d2h;              /* edge columns device -> host                                  */
   float ms_filter;           /* recombination filter (K4), only when filter != 0             */
+  float tc_sweep;            /* 1 if the tile sweep launches ran on the tensor cores (k_sweep_tc) */
 } tracs_stats_t;
 
 /* Options shared by the matrix-input entry points. Zero-initialise, then set. */

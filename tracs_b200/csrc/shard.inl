@@ -100,16 +100,7 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
     DevBuf<uint32_t> dv(CAND_CAP), dv2(CAND_CAP);
     DevBuf<unsigned long long> counter(1);
     TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
-    static bool attr_set = false;
-    if (!attr_set) {
-      TRACS_CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
-      attr_set = true;
-    }
-    int dev = 0, n_sm = 148, occ = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, SWEEP_THREADS, SWEEP_SMEM);
-    occ = std::max(1, occ);
+    const bool tc_ok = o.sweep_variant != 1 && !g.partial_ambiguity;
     const uint32_t words = std::min<uint32_t>(PREFILTER_WORDS, g.Wp);  // Wp is a multiple of KC
     DevBuf<uint32_t> d_rb(std::max<size_t>(1, plan.my_rb.size())), d_prefix(plan.my_rb.size() + 1);
     size_t k0 = 0;
@@ -132,12 +123,7 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
       a.j_start = (uint32_t)o.j_start; a.dist = o.dist; a.rb_list = d_rb.p; a.tile_prefix = d_prefix.p;
       a.n_rb = (uint32_t)rbs.size(); a.n_tiles = (uint32_t)tiles; a.cb_min = plan.cb_min; a.counter = counter.p;
       a.keys = keys.p; a.dvals = dv.p; a.cap = CAND_CAP; a.one = 1;
-      const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)n_sm * occ);
-      if (grid) {
-        k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
-        g_stats.kernel_launches++;
-        TRACS_CK(cudaGetLastError());
-      }
+      launch_tile_sweep(a, tc_ok, st);
       TRACS_CK(cudaStreamSynchronize(st));  // rbs/prefix are reused by the next cut
       g_stats.n_tiles += tiles;
       g_stats.n_pairs += pairs;

@@ -688,6 +688,31 @@ __global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t
 #include "sweep_tc.inl"
 namespace tracs {
 
+// One launch of the tile sweep over a.n_tiles tiles and a.Wp words: tensor-core kernel when the masks
+// allow its identity (no 2-/3-base codes at variable sites), LOP3/POPC kernel otherwise.
+static void launch_tile_sweep(const SweepArgs &a, bool use_tc, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TRACS_CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+    TRACS_CK(cudaFuncSetAttribute(k_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    attr_set = true;
+  }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (a.n_tiles == 0) return;
+  g_stats.tc_sweep = use_tc ? 1.0f : 0.0f;
+  if (use_tc) {
+    k_sweep_tc<<<(unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)n_sm), TC_THREADS, TC_SMEM, st>>>(a);
+  } else {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, SWEEP_THREADS, SWEEP_SMEM);
+    k_sweep<<<(unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)n_sm * std::max(1, occ)), SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
+  }
+  g_stats.kernel_launches++;
+  TRACS_CK(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
@@ -890,18 +915,6 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, keys.p, keys2.p, dv.p, dv2.p, (int64_t)cap, 0, end_bit, st);
   DevBuf<uint8_t> sort_tmp(sort_tmp_bytes);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    TRACS_CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
-    attr_set = true;
-  }
-  int dev = 0, n_sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, SWEEP_THREADS, SWEEP_SMEM);
-  occ = std::max(1, occ);
-
   // ---- fused transmission likelihood set-up (device table over (d, day difference)) ----------
   bool fuse_trans = false;
   uint32_t DD = 0;
@@ -953,7 +966,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     a.j_start = (uint32_t)j_start; a.dist = o.dist; a.rb_list = d_rb.p; a.tile_prefix = d_prefix.p;
     a.n_rb = (uint32_t)rbs.size(); a.n_tiles = n_tiles; a.cb_min = cb_min; a.counter = counter.p;
     a.keys = keys.p; a.dvals = dv.p; a.cap = cap; a.one = 1;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)n_sm * occ);
+    const bool tc_ok = o.sweep_variant != 1 && !ing.partial_ambiguity;  // tensor cores unless forced off / inapplicable
     auto read_counter = [&]() -> unsigned long long {
       unsigned long long c = 0;
       TRACS_CK(cudaMemcpyAsync(&c, counter.p, sizeof c, cudaMemcpyDeviceToHost, st));
@@ -970,9 +983,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     if (try_prefilter) {
       a.Wp = PREFILTER_WORDS;
       T.start();
-      k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
-      S.kernel_launches++;
-      TRACS_CK(cudaGetLastError());
+      launch_tile_sweep(a, tc_ok, st);
       S.ms_sweep += T.stop();
       S.swept_wordpairs += band_pairs[b] * PREFILTER_WORDS;
       const unsigned long long n_cand = read_counter();
@@ -999,23 +1010,12 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     if (!refined) {
       a.Wp = Wp;
       a.keys = keys.p; a.dvals = dv.p;
-      // full-length sweep: the tensor-core kernel (1.4x the LOP3/POPC kernel at C2, profiles/r1_tc_ncu.md) whenever
+      // full-length sweep: the tensor-core kernel (2.0x the LOP3/POPC kernel at C2, profiles/r1_tc_ncu.md) whenever
       // the masks allow its identity; variant 1 forces the LOP3/POPC kernel, variant 2 insists on tensor cores
-      const bool use_tc = o.sweep_variant == 2 || (o.sweep_variant == 0 && !ing.partial_ambiguity && Wp >= 64);
       if (o.sweep_variant == 2 && ing.partial_ambiguity)
         throw std::runtime_error("tensor-core sweep requested but the alignment has 2-/3-base IUPAC codes at variable sites");
       T.start();
-      if (use_tc) {
-        static bool tc_attr = false;
-        if (!tc_attr) {
-          TRACS_CK(cudaFuncSetAttribute(k_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-          tc_attr = true;
-        }
-        k_sweep_tc<<<(unsigned)std::min<uint64_t>(n_tiles, (uint64_t)n_sm), TC_THREADS, TC_SMEM, st>>>(a);
-      } else
-      k_sweep<<<grid, SWEEP_THREADS, SWEEP_SMEM, st>>>(a);
-      S.kernel_launches++;
-      TRACS_CK(cudaGetLastError());
+      launch_tile_sweep(a, tc_ok, st);
       S.ms_sweep += T.stop();
       S.swept_wordpairs += band_pairs[b] * std::max<uint64_t>(W, 1);  // algorithmic words (padding not counted)
       E = read_counter();
