@@ -90,8 +90,11 @@ __device__ __forceinline__ uint32_t nibbles_all_ones(uint32_t x) {
 
 __global__ void __launch_bounds__(PACK_THREADS)
 k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
-       uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/) {
+       uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/,
+       uint32_t *__restrict__ ncount) {
   extern __shared__ __align__(256) char lut[];
+  __shared__ uint32_t s_ncnt[PACK_SCHUNK];  // N count of this CTA's 16 K sites, per sample of the chunk
+  for (int i = threadIdx.x; i < PACK_SCHUNK; i += PACK_THREADS) s_ncnt[i] = 0;
   for (int i = threadIdx.x; i < 256 * 32; i += PACK_THREADS) {
     const uint32_t m = base_mask(i >> 5);
     *reinterpret_cast<uint32_t *>(lut + ((i >> 5) << 8) + ((i & 31) << 2)) = m * 0x1111u | (m == 15u ? 0xFFFF0000u : 0u);
@@ -146,6 +149,10 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch,
         __stcs(nplane + s * npitch + w, isn);
         // block summary: one bit per 4 words (128 sites), one byte per warp (1024 sites)
         uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
+        if (nz) {  // per-sample N count: warp sum -> shared counter (most warps see no N at all)
+          const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, __popc(isn));
+          if (lane == 0) atomicAdd(&s_ncnt[s - s0], wsum);
+        }
         if (lane == 0) {
           uint32_t t2 = nz | (nz >> 1);
           t2 |= (t2 >> 2);
@@ -155,6 +162,9 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch,
       }
     }
   }
+  __syncthreads();
+  for (uint64_t i = threadIdx.x; i < s1 - s0; i += PACK_THREADS)
+    if (s_ncnt[i]) atomicAdd(ncount + s0 + i, s_ncnt[i]);
   if (has_sites) {
     // sites >= L in the last word must not look variable: force their nibbles non-zero
     if (valid != 0xFFFFFFFFu) {
@@ -171,21 +181,6 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch,
     if (acc2 != ~0u) atomicAnd(cm + 2, acc2);
     if (acc3 != ~0u) atomicAnd(cm + 3, acc3);
   }
-}
-
-// per-sample N count: one CTA per sample
-__global__ void k_ncount(const uint32_t *__restrict__ nplane, uint64_t npitch, uint32_t *__restrict__ ncount) {
-  const uint64_t s = blockIdx.x;
-  const uint4 *row = reinterpret_cast<const uint4 *>(nplane + s * npitch);
-  uint32_t c = 0;
-  for (uint64_t i = threadIdx.x; i < npitch / 4; i += blockDim.x) {
-    uint4 v = __ldg(row + i);
-    c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-  }
-  typedef cub::BlockReduce<uint32_t, 256> BR;
-  __shared__ typename BR::TempStorage tmp;
-  uint32_t tot = BR(tmp).Sum(c);
-  if (threadIdx.x == 0) ncount[s] = tot;
 }
 
 // site s is variable iff its column-AND nibble is 0
@@ -761,13 +756,10 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
       TRACS_CK(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PACK_SMEM));
       pack_attr = true;
     }
-    k_pack<<<grid, PACK_THREADS, PACK_SMEM, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch);
+    TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
+    k_pack<<<grid, PACK_THREADS, PACK_SMEM, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p);
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
-    if (want_n) {
-      k_ncount<<<(unsigned)n, 256, 0, st>>>(nplane.p, npitch, ncount.p);
-      S.kernel_launches++;
-    }
   } else {
     TRACS_CK(cudaMemsetAsync(nplane.p, 0, nplane.n * sizeof(uint32_t), st));
     TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
