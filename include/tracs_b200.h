@@ -160,6 +160,12 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
 int tracs_site_shard_partials(void *handle, const uint64_t *dev_keys, size_t n_keys, uint32_t *dev_d, uint32_t *dev_union);
 int tracs_site_shard_close(void *handle);
 
+/* Single-linkage clusters of the thresholded edge list = connected components (what tracs/cluster.py:126-129
+ * asks scipy for). a/b: edge endpoints (node ids < n_nodes), labels: n_nodes entries, numbered like
+ * scipy.sparse.csgraph.connected_components (by the smallest node of each component). Runs on the device. */
+int tracs_connected_components(const uint64_t *a, const uint64_t *b, size_t n_edges, size_t n_nodes, uint32_t *labels,
+                               size_t *n_components);
+
 const char *tracs_last_error(void);
 int tracs_last_stats(tracs_stats_t *out);
 int tracs_device_count(void);

@@ -96,6 +96,13 @@ def main():
         sys.argv = ["", "--msa", os.path.join(HERE, "cli_combined.fasta.gz"), "-o", os.path.join(HERE, "cli_%s.csv" % tag),
                     "--snp_threshold", "40", "-t", "2"] + extra
         distance_main()
+    # the reference's tracs/cluster.py (pure Python + scipy) on the CSV just written
+    import importlib
+    import tracs.cluster as ref_cluster
+    for tag, thr, dist in (("snp10", 10, "snp"), ("ek5", 5, "expectedK"), ("direct", 0.05, "direct")):
+        importlib.reload(ref_cluster)  # fresh function-static name table per run (tracs/cluster.py:11-21)
+        sys.argv = ["", "-d", os.path.join(HERE, "cli_meta.csv"), "-o", os.path.join(HERE, "cluster_%s.csv" % tag), "-c", str(thr), "-D", dist]
+        ref_cluster.main()
     # crafted KAT from the reference's tests/test_trans_distance.py
     with open(os.path.join(HERE, "kat.fasta"), "w") as f:
         f.write(">seq1\nACGTACGTAC\n>seq2\nACGTACGTAN\n>seq3\nACGTACGTGG\n")

@@ -142,3 +142,29 @@ def test_config4_min_over_references(tmp_path):
         c_any = comps([k for k, d in any_rows if d <= thr])
         c_min = comps([k for k, v in got_map.items() if v <= thr])
         assert np.array_equal(c_any, c_min)
+
+
+def test_connected_components_match_scipy():
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    rng = np.random.default_rng(11)
+    for n, m in ((1, 0), (10, 0), (50, 30), (2000, 1500), (20000, 30000), (5000, 200000)):
+        a = rng.integers(0, n, m).astype(np.uint64)
+        b = rng.integers(0, n, m).astype(np.uint64)
+        nc, lab = tracs_b200.connected_components(a, b, n)
+        g = csr_matrix((np.ones(m), (a.astype(np.int64), b.astype(np.int64))), shape=(n, n))
+        enc, elab = connected_components(g, directed=False)
+        assert nc == enc and lab.tolist() == elab.tolist()
+    with pytest.raises(IndexError):
+        tracs_b200.connected_components(np.array([5], np.uint64), np.array([1], np.uint64), 3)
+
+
+@pytest.mark.parametrize("tag,thr,dist", [("snp10", 10, "snp"), ("ek5", 5, "expectedK"), ("direct", 0.05, "direct")])
+def test_cluster_stage_matches_reference(tmp_path, tag, thr, dist):
+    # distances by our driver on the GPU, clusters by our cluster stage; golden = reference tracs/cluster.py on the reference CSV
+    from tracs_b200 import cluster, distance
+    dcsv, ccsv = str(tmp_path / "d.csv"), str(tmp_path / "c.csv")
+    distance.distance([os.path.join(GOLD, "cli_combined.fasta.gz")], dcsv, snp_threshold=40, n_cpu=1,
+                      metadata=os.path.join(GOLD, "cli_dates.csv"), trans_threshold=100.0)
+    cluster.cluster(dcsv, ccsv, thr, dist)
+    assert open(ccsv).read() == open(os.path.join(GOLD, "cluster_%s.csv" % tag)).read()

@@ -7,7 +7,7 @@ import os
 import sys
 
 from .api import (pairsnp, trans_dist, lprob_k_given_N, calculate_posteriors, pairsnp_matrix, pairsnp_device,
-                  min_over_refs, synth_device, int_peak, last_stats, read_fasta, shard_rowblocks, INT32_MAX)
+                  min_over_refs, synth_device, int_peak, last_stats, read_fasta, shard_rowblocks, connected_components, INT32_MAX)
 
 DROPIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
 

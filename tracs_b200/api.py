@@ -133,6 +133,17 @@ def synth_device(dev_ptr, n, L, pitch, seed=1, p_var=0.01, n_clusters=20, mu=5.0
     _lib.check(_lib.lib().tracs_synth_device(C.byref(cfg), C.c_void_p(dev_ptr), C.c_void_p(dev_days) if dev_days else None))
 
 
+def connected_components(a, b, n_nodes):
+    """Labels of the connected components of an undirected edge list, numbered like
+    scipy.sparse.csgraph.connected_components. Returns (n_components, labels uint32[n_nodes])."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    labels = np.zeros(int(n_nodes), np.uint32)
+    nc = C.c_size_t(0)
+    _lib.check(_lib.lib().tracs_connected_components(a.ctypes.data, b.ctypes.data, a.size, int(n_nodes), labels.ctypes.data, C.byref(nc)))
+    return nc.value, labels
+
+
 def read_fasta(path, n_threads=1):
     """FASTA/FASTQ(.gz) -> (uint8[n][L] ASCII matrix, names). Host only (the loader half of pairsnp)."""
     seqs = C.POINTER(C.c_uint8)()

@@ -603,6 +603,89 @@ int tracs_min_over_refs(const uint64_t *a, const uint64_t *b, const double *val,
   });
 }
 
+// ---- single-linkage clusters = connected components (tracs/cluster.py:104-129) -------------------------
+namespace tracs {
+__device__ __forceinline__ uint32_t cc_find(uint32_t *parent, uint32_t v) {
+  // path halving
+  uint32_t p = parent[v];
+  while (p != v) {
+    const uint32_t gp = parent[p];
+    if (gp != p) parent[v] = gp;
+    v = p;
+    p = gp;
+  }
+  return v;
+}
+__global__ void k_cc_init(uint32_t *parent, uint32_t n) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) parent[v] = v;
+}
+// hook the larger root under the smaller one: the root of a finished component is its smallest node
+__global__ void k_cc_hook(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint64_t E, uint32_t *parent) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  uint32_t ru = cc_find(parent, (uint32_t)a[e]), rv = cc_find(parent, (uint32_t)b[e]);
+  while (ru != rv) {
+    const uint32_t hi = max(ru, rv), lo = min(ru, rv);
+    const uint32_t old = atomicCAS(parent + hi, hi, lo);
+    if (old == hi) break;          // hooked
+    ru = cc_find(parent, old);     // somebody else hooked hi first: continue from its new root
+    rv = lo;
+    rv = cc_find(parent, rv);
+  }
+}
+__global__ void k_cc_flatten(uint32_t *parent, uint32_t n, uint8_t *is_root) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  uint32_t r = v;
+  while (parent[r] != r) r = parent[r];
+  parent[v] = r;
+  is_root[v] = (r == v);
+}
+__global__ void k_cc_label(const uint32_t *__restrict__ parent, const uint32_t *__restrict__ root_rank, uint32_t n,
+                           uint32_t *__restrict__ labels) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) labels[v] = root_rank[parent[v]];
+}
+}  // namespace tracs
+
+int tracs_connected_components(const uint64_t *a, const uint64_t *b, size_t n_edges, size_t n_nodes, uint32_t *labels,
+                               size_t *n_components) {
+  return guarded([&] {
+    require_device();
+    *n_components = 0;
+    if (n_nodes == 0) return;
+    if (n_nodes >= (1ull << 32)) throw std::runtime_error("too many nodes");
+    for (size_t e = 0; e < n_edges; ++e)
+      if (a[e] >= n_nodes || b[e] >= n_nodes) throw std::out_of_range("edge endpoint out of range");
+    const uint32_t n = (uint32_t)n_nodes;
+    DevBuf<uint32_t> parent(n), rank(n), lab(n);
+    DevBuf<uint8_t> is_root(n);
+    DevBuf<uint64_t> da(std::max<size_t>(1, n_edges)), db(std::max<size_t>(1, n_edges));
+    if (n_edges) {
+      TRACS_CK(cudaMemcpy(da.p, a, n_edges * 8, cudaMemcpyHostToDevice));
+      TRACS_CK(cudaMemcpy(db.p, b, n_edges * 8, cudaMemcpyHostToDevice));
+    }
+    k_cc_init<<<(n + 255) / 256, 256>>>(parent.p, n);
+    if (n_edges) k_cc_hook<<<(unsigned)((n_edges + 255) / 256), 256>>>(da.p, db.p, n_edges, parent.p);
+    k_cc_flatten<<<(n + 255) / 256, 256>>>(parent.p, n, is_root.p);
+    // label of a component = rank of its root (= its smallest node) among all roots: the numbering
+    // scipy.sparse.csgraph.connected_components produces (components discovered from node 0 upwards)
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, is_root.p, rank.p, (int64_t)n);
+    DevBuf<uint8_t> tmp(tb);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, is_root.p, rank.p, (int64_t)n);
+    k_cc_label<<<(n + 255) / 256, 256>>>(parent.p, rank.p, n, lab.p);
+    TRACS_CK(cudaGetLastError());
+    TRACS_CK(cudaMemcpy(labels, lab.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    uint32_t last_rank = 0;
+    uint8_t last_root = 0;
+    TRACS_CK(cudaMemcpy(&last_rank, rank.p + (n - 1), 4, cudaMemcpyDeviceToHost));
+    TRACS_CK(cudaMemcpy(&last_root, is_root.p + (n - 1), 1, cudaMemcpyDeviceToHost));
+    *n_components = (size_t)last_rank + last_root;
+  });
+}
+
 int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev_days) {
   return guarded([&] {
     require_device();
