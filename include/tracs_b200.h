@@ -166,6 +166,16 @@ int tracs_site_shard_close(void *handle);
 int tracs_connected_components(const uint64_t *a, const uint64_t *b, size_t n_edges, size_t n_nodes, uint32_t *labels,
                                size_t *n_components);
 
+/* Native writer of the distance CSV (the per-edge Python loop of tracs/distance.py:206-258): same header,
+ * column order and quirks (NA columns without metadata, `NA` in the filtered column with metadata but no
+ * filter, rows with expected K above the -K threshold dropped, floats printed like Python's repr).
+ * e: edges of one MSA (p0_log/eK/datediff set when the likelihood was computed); names: sample names. Host only. */
+int tracs_write_distance_csv(const char *path, int append, const tracs_edges_t *e, const char *const *names, size_t n_names,
+                             const char *msa_label, int has_trans, int filter_on, int use_k_threshold, double k_threshold,
+                             size_t *rows_written);
+/* Python-repr formatting of a double (what the writer uses); buf >= 32 bytes; returns the length. */
+size_t tracs_float_repr(double v, char *buf);
+
 const char *tracs_last_error(void);
 int tracs_last_stats(tracs_stats_t *out);
 int tracs_device_count(void);

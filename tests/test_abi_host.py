@@ -158,3 +158,55 @@ def test_shard_dealing_covers_and_balances():
         work = [sum(n_rb - int(rb) for rb in p) for p in parts]
         if n_rb >= 4 * world:
             assert max(work) - min(work) <= 2 * world + n_rb % (2 * world) * world
+
+
+def test_float_repr_matches_python():
+    import math, random, struct
+    L = _lib.lib()
+    buf = C.create_string_buffer(64)
+
+    def r(v):
+        L.tracs_float_repr(v, buf)
+        return buf.value.decode()
+
+    for v in [0.0, -0.0, 1.0, 0.1, 1e-4, 1e-5, 1.5e-5, 1e15, 1e16, 1.5e16, 1e22, 0.002737907006988508, float("inf"), -float("inf"),
+              5e-324, 1.7976931348623157e308, 100.0, 12345.678, 0.23794988406662973]:
+        assert r(v) == repr(v)
+    assert r(float("nan")) == "nan"
+    random.seed(3)
+    for _ in range(20000):
+        v = struct.unpack("d", struct.pack("Q", random.getrandbits(64)))[0]
+        if not math.isnan(v):
+            assert r(v) == repr(v)
+        w = random.random() * 10 ** random.randint(-8, 18)
+        assert r(w) == repr(w)
+
+
+def test_native_csv_writer_layout(tmp_path):
+    # host-only: build an edge table by hand and check every quirk of tracs/distance.py:206-258
+    e = _lib.Edges()
+    n = 3
+    rows = (C.c_uint64 * n)(0, 0, 1)
+    cols = (C.c_uint64 * n)(1, 2, 2)
+    dist = (C.c_uint64 * n)(0, 2, 1)
+    filt = (C.c_uint64 * n)(0, 1, 1)
+    ncomp = (C.c_uint64 * n)(9, 10, 9)
+    import math
+    lp = [math.log(0.25), math.log(0.5), math.log(0.125)]
+    p0 = (C.c_double * n)(*lp)
+    eK = (C.c_double * n)(2.5, 12.0, 4.0)
+    dt = (C.c_double * n)(0.002737907006988508, 0.002737907006988508, 0.0)
+    names = (C.c_char_p * 3)(b"seq1", b"seq2", b"seq3")
+    e.n_edges, e.rows, e.cols, e.dist, e.filt, e.ncomp = n, rows, cols, dist, filt, ncomp
+    e.p0_log, e.eK, e.datediff = p0, eK, dt
+    out = str(tmp_path / "o.csv")
+    w = C.c_size_t(0)
+    L = _lib.lib()
+    _lib.check(L.tracs_write_distance_csv(out.encode(), 0, C.byref(e), names, 3, b"kat", 1, 0, 1, 10.0, C.byref(w)))
+    lines = open(out).read().splitlines()
+    assert w.value == 2 and lines[0].startswith("sampleA,sampleB,date difference,SNP distance")
+    assert lines[1] == "seq1,seq2,0.002737907006988508,0,%r,2.5,NA,9,kat" % math.exp(lp[0])  # NA: metadata, no filter
+    assert lines[2] == "seq2,seq3,0.0,1,%r,4.0,NA,9,kat" % math.exp(lp[2])                   # eK = 12 > K = 10 dropped
+    _lib.check(L.tracs_write_distance_csv(out.encode(), 1, C.byref(e), names, 3, b"k2", 0, 0, 0, 0.0, C.byref(w)))
+    lines = open(out).read().splitlines()
+    assert w.value == 3 and lines[3] == "seq1,seq2,NA,0,NA,NA,0,9,k2"             # no metadata: NA columns, filtered column = 0

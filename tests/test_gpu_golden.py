@@ -168,3 +168,18 @@ def test_cluster_stage_matches_reference(tmp_path, tag, thr, dist):
                       metadata=os.path.join(GOLD, "cli_dates.csv"), trans_threshold=100.0)
     cluster.cluster(dcsv, ccsv, thr, dist)
     assert open(ccsv).read() == open(os.path.join(GOLD, "cluster_%s.csv" % tag)).read()
+
+
+@pytest.mark.parametrize("tag,extra", [("meta", dict(metadata=os.path.join(GOLD, "cli_dates.csv"), trans_threshold=100.0)), ("nometa", {})])
+def test_distance_cli_native_csv(tmp_path, tag, extra):
+    # the C writer produces the same file as the Python loop of the mirror (and hence as the reference, see above)
+    from tracs_b200 import distance
+    a, b = str(tmp_path / "py.csv"), str(tmp_path / "native.csv")
+    distance.distance([os.path.join(GOLD, "cli_combined.fasta.gz")], a, snp_threshold=40, **extra)
+    distance.distance([os.path.join(GOLD, "cli_combined.fasta.gz")], b, snp_threshold=40, native_csv=True, **extra)
+    ra, rb = _rows(a), _rows(b)
+    assert len(ra) == len(rb) and ra[0] == rb[0]
+    for x, y in zip(ra[1:], rb[1:]):
+        assert x[:4] == y[:4] and x[5:] == y[5:]
+        if x[4] != "NA":   # exp() of numpy vs libm may differ in the last printed digit
+            assert abs(float(x[4]) - float(y[4])) <= 1e-15 * abs(float(x[4]))

@@ -50,7 +50,8 @@ SYMBOLS = ["tracs_pairsnp", "tracs_pairsnp_host", "tracs_pairsnp_device", "tracs
            "tracs_last_stats", "tracs_device_count", "tracs_trim", "tracs_set_device", "tracs_synth_device", "tracs_dev_alloc",
            "tracs_dev_free", "tracs_host_alloc_pinned", "tracs_host_free_pinned", "tracs_memcpy_d2h",
            "tracs_memcpy_h2d", "tracs_int_peak", "tracs_read_fasta", "tracs_free_fasta", "tracs_shard_rowblocks",
-           "tracs_site_shard_open", "tracs_site_shard_partials", "tracs_site_shard_close", "tracs_connected_components"]
+           "tracs_site_shard_open", "tracs_site_shard_partials", "tracs_site_shard_close", "tracs_connected_components",
+           "tracs_write_distance_csv", "tracs_float_repr"]
 
 _lib = None
 
@@ -90,6 +91,10 @@ def lib():
         L.tracs_site_shard_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.tracs_site_shard_close.argtypes = [C.c_void_p]
         L.tracs_connected_components.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.tracs_write_distance_csv.argtypes = [C.c_char_p, C.c_int, C.POINTER(Edges), C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p, C.c_int,
+                                               C.c_int, C.c_int, C.c_double, C.POINTER(C.c_size_t)]
+        L.tracs_float_repr.argtypes = [C.c_double, C.c_char_p]
+        L.tracs_float_repr.restype = C.c_size_t
         L.tracs_shard_rowblocks.argtypes = [C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <charconv>
 #include <functional>
 #include <numeric>
 #include <map>
@@ -683,6 +684,95 @@ int tracs_connected_components(const uint64_t *a, const uint64_t *b, size_t n_ed
     TRACS_CK(cudaMemcpy(&last_rank, rank.p + (n - 1), 4, cudaMemcpyDeviceToHost));
     TRACS_CK(cudaMemcpy(&last_root, is_root.p + (n - 1), 1, cudaMemcpyDeviceToHost));
     *n_components = (size_t)last_rank + last_root;
+  });
+}
+
+// ---- native CSV writer for the distance stage (tracs/distance.py:206-258) --------------------------------
+namespace tracs {
+// Python's repr(float): shortest digits that round-trip; fixed notation while -4 < decpt <= 16, else d.ddde+XX
+static size_t py_float_repr(double v, char *out) {
+  if (std::isnan(v)) { memcpy(out, "nan", 3); return 3; }
+  if (std::isinf(v)) { const char *t = v < 0 ? "-inf" : "inf"; size_t n = strlen(t); memcpy(out, t, n); return n; }
+  char tmp[64];
+  auto r = std::to_chars(tmp, tmp + sizeof tmp, v, std::chars_format::scientific);
+  *r.ptr = 0;
+  char *o = out;
+  const char *p = tmp;
+  if (*p == '-') *o++ = *p++;
+  char digits[32];
+  int nd = 0;
+  for (; *p && *p != 'e'; ++p)
+    if (*p != '.') digits[nd++] = *p;
+  const int decpt = atoi(p + 1) + 1;
+  while (nd > 1 && digits[nd - 1] == '0') --nd;  // to_chars is already shortest; be safe
+  if (decpt > 16 || decpt < -3) {
+    *o++ = digits[0];
+    if (nd > 1) { *o++ = '.'; memcpy(o, digits + 1, nd - 1); o += nd - 1; }
+    const int e = decpt - 1;
+    o += sprintf(o, "e%c%02d", e < 0 ? '-' : '+', e < 0 ? -e : e);
+  } else if (decpt <= 0) {
+    *o++ = '0'; *o++ = '.';
+    for (int k = 0; k < -decpt; ++k) *o++ = '0';
+    memcpy(o, digits, nd); o += nd;
+  } else if (decpt >= nd) {
+    memcpy(o, digits, nd); o += nd;
+    for (int k = nd; k < decpt; ++k) *o++ = '0';
+    *o++ = '.'; *o++ = '0';
+  } else {
+    memcpy(o, digits, decpt); o += decpt;
+    *o++ = '.';
+    memcpy(o, digits + decpt, nd - decpt); o += nd - decpt;
+  }
+  return (size_t)(o - out);
+}
+}  // namespace tracs
+
+size_t tracs_float_repr(double v, char *buf) {
+  const size_t n = tracs::py_float_repr(v, buf);
+  buf[n] = 0;
+  return n;
+}
+
+int tracs_write_distance_csv(const char *path, int append, const tracs_edges_t *e, const char *const *names, size_t n_names,
+                             const char *msa_label, int has_trans, int filter_on, int use_k_threshold, double k_threshold,
+                             size_t *rows_written) {
+  return guarded([&] {
+    if (rows_written) *rows_written = 0;
+    FILE *f = fopen(path, append ? "ab" : "wb");
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    static const char HEADER[] =
+        "sampleA,sampleB,date difference,SNP distance,transmission distance,expected K,filtered SNP distance,sites considered,MSA file\n";
+    std::string buf;
+    buf.reserve(1 << 22);
+    if (!append) buf += HEADER;
+    char num[96];
+    size_t written = 0;
+    const bool trans = has_trans && e->p0_log && e->eK && e->datediff;
+    for (size_t k = 0; k < e->n_edges; ++k) {
+      if (trans && use_k_threshold && !(k_threshold >= e->eK[k])) continue;  // tracs/distance.py:222
+      if (e->rows[k] >= n_names || e->cols[k] >= n_names) throw std::out_of_range("edge index beyond the name list");
+      buf += names[e->rows[k]]; buf += ',';
+      buf += names[e->cols[k]]; buf += ',';
+      if (trans) { buf.append(num, tracs::py_float_repr(e->datediff[k], num)); } else buf += "NA";
+      buf += ',';
+      buf.append(num, (size_t)sprintf(num, "%llu", (unsigned long long)e->dist[k])); buf += ',';
+      if (trans) { buf.append(num, tracs::py_float_repr(exp(e->p0_log[k]), num)); } else buf += "NA";
+      buf += ',';
+      if (trans) { buf.append(num, tracs::py_float_repr(e->eK[k], num)); } else buf += "NA";
+      buf += ',';
+      // with metadata and no filter the reference writes NA, otherwise the number (zeros when the filter is off)
+      if (trans && !filter_on) buf += "NA";
+      else buf.append(num, (size_t)sprintf(num, "%llu", (unsigned long long)e->filt[k]));
+      buf += ',';
+      buf.append(num, (size_t)sprintf(num, "%llu", (unsigned long long)e->ncomp[k])); buf += ',';
+      buf += msa_label;
+      buf += '\n';
+      ++written;
+      if (buf.size() > (1u << 22) - 4096) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
+    }
+    fwrite(buf.data(), 1, buf.size(), f);
+    if (fclose(f) != 0) throw std::runtime_error("write error");
+    if (rows_written) *rows_written = written;
   });
 }
 

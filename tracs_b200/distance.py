@@ -39,9 +39,51 @@ def date_differences(rows, cols, names, dates):
     return np.abs(t[np.asarray(rows, dtype=np.int64)] - t[np.asarray(cols, dtype=np.int64)]) / SECONDS_IN_YEAR
 
 
+def _distance_native(msa_files, output_file, msa_db, dates, snp_threshold, recomb_filter, clock_rate, trans_rate, trans_threshold,
+                     precision, n_cpu):
+    """Same stage with the edge columns kept in C arrays end to end: tracs_pairsnp -> tracs_trans_dist ->
+    tracs_write_distance_csv (no per-edge Python objects)."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    for k, msa in enumerate(msa_files):
+        fastas = [os.fspath(msa)] + ([os.fspath(msa_db)] if msa_db is not None else [])
+        paths = (C.c_char_p * len(fastas))(*[os.fsencode(p) for p in fastas])
+        e = _lib.Edges()
+        _lib.check(L.tracs_pairsnp(paths, len(fastas), int(n_cpu), int(snp_threshold), int(bool(recomb_filter)), C.byref(e)))
+        keep = []
+        try:
+            n = e.n_edges
+            names = [e.names[i].decode() for i in range(e.n_names)]
+            has_trans = dates is not None and n > 0
+            if has_trans:
+                rows = np.ctypeslib.as_array(e.rows, shape=(n,))
+                cols = np.ctypeslib.as_array(e.cols, shape=(n,))
+                src = np.ctypeslib.as_array(e.filt if recomb_filter else e.dist, shape=(n,))
+                dt = np.ascontiguousarray(date_differences(rows, cols, names, dates), dtype=np.float64)
+                p0, eK = api.trans_dist_np(src.astype(np.int32), dt, clock_rate, trans_rate, precision)
+                keep = [dt, p0, eK]
+                e.datediff = dt.ctypes.data_as(C.POINTER(C.c_double))
+                e.p0_log = p0.ctypes.data_as(C.POINTER(C.c_double))
+                e.eK = eK.ctypes.data_as(C.POINTER(C.c_double))
+            ref = os.path.basename(msa).split(".")[0].replace("_combined", "")
+            written = C.c_size_t(0)
+            _lib.check(L.tracs_write_distance_csv(os.fsencode(output_file), int(k > 0), C.byref(e), e.names, e.n_names, ref.encode(),
+                                                  int(has_trans), int(bool(recomb_filter)), int(trans_threshold is not None),
+                                                  float(trans_threshold if trans_threshold is not None else 0.0), C.byref(written)))
+        finally:
+            # the likelihood columns are NumPy-owned: detach them before the library frees its own arrays
+            e.datediff = e.p0_log = e.eK = C.POINTER(C.c_double)()
+            L.tracs_edges_free(C.byref(e))
+            del keep
+
+
 def distance(msa_files, output_file, msa_db=None, metadata=None, snp_threshold=2147483647, recomb_filter=False,
-             clock_rate=1e-3 * 29903, trans_rate=73.0, trans_threshold=None, precision=0.01, n_cpu=1):
+             clock_rate=1e-3 * 29903, trans_rate=73.0, trans_threshold=None, precision=0.01, n_cpu=1, native_csv=False):
     dates = read_dates(metadata) if metadata is not None else None
+    if native_csv:
+        return _distance_native(msa_files, output_file, msa_db, dates, snp_threshold, recomb_filter, clock_rate, trans_rate,
+                                trans_threshold, precision, n_cpu)
     with open(output_file, "w") as out:
         out.write(HEADER)
         for msa in msa_files:
@@ -77,6 +119,7 @@ def main(argv=None):
     ap.add_argument("-K", "--trans_threshold", type=float, default=None)
     ap.add_argument("--precision", type=float, default=0.01)
     ap.add_argument("-t", "--threads", dest="n_cpu", type=int, default=1)
+    ap.add_argument("--native-csv", dest="native_csv", action="store_true", help="write the CSV from C (no per-edge Python objects)")
     a = ap.parse_args(argv)
     distance(**vars(a))
 
