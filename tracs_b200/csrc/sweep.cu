@@ -110,56 +110,73 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch,
   const bool in_row = w < npitch;
   const bool has_sites = site0 < L;
   uint32_t acc0 = ~0u, acc1 = ~0u, acc2 = ~0u, acc3 = ~0u;
-  uint32_t valid = 0xFFFFFFFFu;
+  uint32_t valid = has_sites ? 0xFFFFFFFFu : 0u;
   if (has_sites && L - site0 < 32) valid = (1u << (uint32_t)(L - site0)) - 1u;
-  // PACK_BATCH samples per trip: all global loads of the batch are issued before any table lookup,
-  // so every thread keeps 2 * PACK_BATCH 16-byte loads in flight (the kernel is HBM-latency bound).
-  for (uint64_t sb = s0; sb < s1; sb += PACK_BATCH) {
-    uint4 va[PACK_BATCH], vb[PACK_BATCH];
-#pragma unroll
-    for (int t = 0; t < PACK_BATCH; ++t) {
-      if (has_sites && sb + t < s1) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(seqs + (sb + t) * pitch + site0);
-        va[t] = __ldcs(src);
-        vb[t] = __ldcs(src + 1);
-      } else {
-        va[t] = vb[t] = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);  // 'N': neutral for the column AND
+  // One sample's 32 sites: table lookups, column AND, is-N word, N count and block summary. Lanes past the
+  // end of the alignment carry 'N' bytes and valid == 0, so every lane of a warp runs the same code.
+  // Running pointers (no 64-bit index arithmetic per sample); the summary byte is only computed and stored
+  // when the warp saw an N at all (the buffer is pre-zeroed).
+  auto one_sample = [&](const uint4 &a, const uint4 &b, uint32_t *np, uint8_t *sp, uint32_t *cnt) {
+    const uint32_t x0 = lut4(lut, lane4, a.x), x1 = lut4(lut, lane4, a.y), x2 = lut4(lut, lane4, a.z), x3 = lut4(lut, lane4, a.w);
+    const uint32_t x4 = lut4(lut, lane4, b.x), x5 = lut4(lut, lane4, b.y), x6 = lut4(lut, lane4, b.z), x7 = lut4(lut, lane4, b.w);
+    // eight sites per register: 4-bit masks
+    acc0 &= __byte_perm(x0, x1, 0x5410);
+    acc1 &= __byte_perm(x2, x3, 0x5410);
+    acc2 &= __byte_perm(x4, x5, 0x5410);
+    acc3 &= __byte_perm(x6, x7, 0x5410);
+    // byte 2 of each pair: is-N flags of eight sites
+    const uint32_t n0 = bsel(x0, x1, 0x000F0000u), n1 = bsel(x2, x3, 0x000F0000u);
+    const uint32_t n2 = bsel(x4, x5, 0x000F0000u), n3 = bsel(x6, x7, 0x000F0000u);
+    const uint32_t isn = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n2, n3, 0x0062), 0x5410) & valid;
+    __stcs(np, isn);
+    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
+    if (nz) {
+      const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, __popc(isn));
+      if (lane == 0) {
+        atomicAdd(cnt, wsum);
+        // block summary: one bit per 4 words (128 sites), one byte per warp (1024 sites)
+        uint32_t t2 = nz | (nz >> 1);
+        t2 |= (t2 >> 2);
+        t2 &= 0x11111111u;
+        *sp = (uint8_t)nibbles_all_ones(t2 * 0xFu);
       }
     }
+  };
+  const uint4 kN = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);  // 'N': neutral for the column AND
+  if (in_row) {  // warp-uniform: npitch is a multiple of 32 words
+    const uint8_t *src = seqs + s0 * pitch + (has_sites ? site0 : 0);
+    uint32_t *np = nplane + s0 * npitch + w;
+    uint8_t *sp = nsum + s0 * spitch + (w >> 5);
+    uint32_t *cnt = s_ncnt;
+    uint64_t sb = s0;
+    // PACK_BATCH samples per trip: all global loads of the batch are issued before any table lookup,
+    // so every thread keeps 2 * PACK_BATCH 16-byte loads in flight
+    for (; sb + PACK_BATCH <= s1; sb += PACK_BATCH) {
+      uint4 va[PACK_BATCH], vb[PACK_BATCH];
 #pragma unroll
-    for (int t = 0; t < PACK_BATCH; ++t) {
-      const uint64_t s = sb + t;
-      if (s >= s1) break;
-      uint32_t isn = 0;
+      for (int t = 0; t < PACK_BATCH; ++t) {
+        if (has_sites) {
+          va[t] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch));
+          vb[t] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch) + 1);
+        } else {
+          va[t] = vb[t] = kN;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < PACK_BATCH; ++t) one_sample(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t);
+      src += (size_t)PACK_BATCH * pitch;
+      np += (size_t)PACK_BATCH * npitch;
+      sp += (size_t)PACK_BATCH * spitch;
+      cnt += PACK_BATCH;
+    }
+    for (; sb < s1; ++sb) {  // tail of the chunk
+      uint4 va = kN, vb = kN;
       if (has_sites) {
-        const uint4 a = va[t], b = vb[t];
-        const uint32_t x0 = lut4(lut, lane4, a.x), x1 = lut4(lut, lane4, a.y), x2 = lut4(lut, lane4, a.z), x3 = lut4(lut, lane4, a.w);
-        const uint32_t x4 = lut4(lut, lane4, b.x), x5 = lut4(lut, lane4, b.y), x6 = lut4(lut, lane4, b.z), x7 = lut4(lut, lane4, b.w);
-        // eight sites per register: 4-bit masks
-        acc0 &= __byte_perm(x0, x1, 0x5410);
-        acc1 &= __byte_perm(x2, x3, 0x5410);
-        acc2 &= __byte_perm(x4, x5, 0x5410);
-        acc3 &= __byte_perm(x6, x7, 0x5410);
-        // byte 2 of each pair: is-N flags of eight sites
-        const uint32_t n0 = bsel(x0, x1, 0x000F0000u), n1 = bsel(x2, x3, 0x000F0000u);
-        const uint32_t n2 = bsel(x4, x5, 0x000F0000u), n3 = bsel(x6, x7, 0x000F0000u);
-        isn = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n2, n3, 0x0062), 0x5410) & valid;
+        va = __ldcs(reinterpret_cast<const uint4 *>(src));
+        vb = __ldcs(reinterpret_cast<const uint4 *>(src) + 1);
       }
-      if (in_row) {
-        __stcs(nplane + s * npitch + w, isn);
-        // block summary: one bit per 4 words (128 sites), one byte per warp (1024 sites)
-        uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
-        if (nz) {  // per-sample N count: warp sum -> shared counter (most warps see no N at all)
-          const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, __popc(isn));
-          if (lane == 0) atomicAdd(&s_ncnt[s - s0], wsum);
-        }
-        if (lane == 0) {
-          uint32_t t2 = nz | (nz >> 1);
-          t2 |= (t2 >> 2);
-          t2 &= 0x11111111u;
-          nsum[s * spitch + (w >> 5)] = (uint8_t)nibbles_all_ones(t2 * 0xFu);
-        }
-      }
+      one_sample(va, vb, np, sp, cnt);
+      src += pitch; np += npitch; sp += spitch; ++cnt;
     }
   }
   __syncthreads();
