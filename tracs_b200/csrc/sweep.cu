@@ -53,30 +53,25 @@ __host__ __device__ inline uint32_t base_mask(uint32_t c) {
 
 // ------------------------------------------------------------------------------------------
 // K0a: pack
-//   thread <-> one 32-site word (32 ASCII bytes) ; loops over a chunk of samples
-//   lut: 256 entries x 32 lanes (lane-private bank => conflict-free byte lookups)
+//   thread <-> one 32-site word (32 ASCII bytes) ; loops over a chunk of samples.
+//   No memory table: PRMT is used as an 8-entry byte table, four lookups per instruction. The index
+//   is the low 3 bits of the base, which tell the plain alphabet apart:
+//       A 001  C 011  G 111  T 100  N 110  - 101        (upper or lower case, bit 5 is ignored)
+//   One table returns the 4-bit mask (+ an is-N flag), a second one the byte the index stands for;
+//   a byte that differs from it (IUPAC 2-/3-base codes, anything else) is repaired from the exact
+//   256-entry table on a rare branch, so the result is exact for every input byte.
+//   Two adjacent words of one sample (8 sites) share one selector register: nibble 2k = word 0
+//   byte k, nibble 2k+1 = word 1 byte k, so every lookup result holds sites (0, 4, 1, 5) or
+//   (2, 6, 3, 7) of the 8-site group. The N-plane word is stored in that fixed site permutation:
+//   its only consumers are population counts of ANDs (k_ncomp, k_shard_partials).
 // ------------------------------------------------------------------------------------------
-constexpr int PACK_THREADS = 512;
+constexpr int PACK_THREADS = 256;
 constexpr int PACK_SCHUNK = 256;
 constexpr int PACK_BATCH = 4;
-// LUT: row c (256 B) holds one 32-bit entry per lane at byte offset lane*4, so the byte address
-// (c << 8) | (lane << 2) is ONE PRMT away from the packed ASCII word and every lane owns a bank.
-// entry = base mask replicated in the four low nibbles | 0xFFFF0000 if the mask is 1111 (N).
-constexpr size_t PACK_SMEM = 256 * 256;
 
 // bit-select: (a & m) | (b & ~m)  -> one LOP3
 __device__ __forceinline__ uint32_t bsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
 
-// four ASCII bytes -> low 16 bits: four 4-bit masks ; bits 16-19 and 20-23: the four is-N flags
-__device__ __forceinline__ uint32_t lut4(const char *lut, uint32_t lane4, uint32_t w) {
-  const uint32_t e0 = *reinterpret_cast<const uint32_t *>(lut + __byte_perm(w, lane4, 0x5504));
-  const uint32_t e1 = *reinterpret_cast<const uint32_t *>(lut + __byte_perm(w, lane4, 0x5514));
-  const uint32_t e2 = *reinterpret_cast<const uint32_t *>(lut + __byte_perm(w, lane4, 0x5524));
-  const uint32_t e3 = *reinterpret_cast<const uint32_t *>(lut + __byte_perm(w, lane4, 0x5534));
-  const uint32_t t01 = bsel(e0, e1, 0x00550F0Fu);
-  const uint32_t t23 = bsel(e2, e3, 0x00550F0Fu);
-  return bsel(t01, t23, 0x003300FFu);
-}
 // bit i of result = nibble i of x is 0xF
 __device__ __forceinline__ uint32_t nibbles_all_ones(uint32_t x) {
   uint32_t t = x & (x >> 1);
@@ -88,20 +83,160 @@ __device__ __forceinline__ uint32_t nibbles_all_ones(uint32_t x) {
   return t;
 }
 
+// mask table indexed by (byte & 7); F = 1111 + the is-N flag in bit 4 + V
+//   000 F   001 A=1   010 F   011 C=2   100 T=8   101 F   110 F   111 G=4
+template <int V> struct PackTab {
+  static constexpr uint32_t F = 0x0Fu | (0x10u << V);
+  static constexpr uint32_t LO = F | (0x01u << 8) | (F << 16) | (0x02u << 24);
+  static constexpr uint32_t HI = 0x08u | (F << 8) | (F << 16) | (0x04u << 24);
+};
+// the byte each index stands for; 000 and 010 stand for nothing (entry with other low bits)
+constexpr uint32_t PACK_E_LO = 0x01u | (0x41u << 8) | (0x01u << 16) | (0x43u << 24);
+constexpr uint32_t PACK_E_HI = 0x54u | (0x2Du << 8) | (0x4Eu << 16) | (0x47u << 24);
+
+// rare path: bytes flagged in d (non-zero byte) get their exact mask from the 256-entry table
+__device__ __noinline__ uint32_t pack_repair(uint32_t o, uint32_t d, uint32_t m, uint32_t flag, const uint8_t *slut) {
+#pragma unroll 1
+  for (int p = 0; p < 32; p += 8) {
+    if ((d >> p) & 0xFFu) {
+      const uint32_t bm = slut[(o >> p) & 0xFFu];
+      const uint32_t nb = bm | (bm == 15u ? flag : 0u);
+      m = (m & ~(0xFFu << p)) | (nb << p);
+    }
+  }
+  return m;
+}
+
+// PRMT with a run-time selector (only selector bits 0-15 are read; bit 3 of every nibble must be 0)
+__device__ __forceinline__ uint32_t tab8(uint32_t lo, uint32_t hi, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
+  return r;
+}
+
+// eight sites (two words of one sample) -> two registers of per-site mask bytes
+template <int V0, int V1>
+__device__ __forceinline__ void pack_unit(uint32_t w1, uint32_t w2, const uint8_t *slut, uint32_t &m1, uint32_t &m2) {
+  const uint32_t z = (w1 & 0x07070707u) | ((w2 << 4) & 0x70707070u);
+  const uint32_t zh = z >> 16;
+  m1 = tab8(PackTab<V0>::LO, PackTab<V0>::HI, z);
+  m2 = tab8(PackTab<V1>::LO, PackTab<V1>::HI, zh);
+  const uint32_t e1 = tab8(PACK_E_LO, PACK_E_HI, z), e2 = tab8(PACK_E_LO, PACK_E_HI, zh);
+  const uint32_t o1 = __byte_perm(w1, w2, 0x5140), o2 = __byte_perm(w1, w2, 0x7362);
+  const uint32_t d1 = (o1 ^ e1) & 0xDFDFDFDFu, d2 = (o2 ^ e2) & 0xDFDFDFDFu;
+  if (__builtin_expect((d1 | d2) != 0u, 0)) {
+    m1 = pack_repair(o1, d1, m1, 0x10u << V0, slut);
+    m2 = pack_repair(o2, d2, m2, 0x10u << V1, slut);
+  }
+}
+
+// N-plane bit of site t (0..31) of a word: see pack_unit / one_sample
+__device__ __forceinline__ uint32_t pack_nbit(uint32_t t) {
+  const uint32_t k = t >> 2, b = t & 3u, j = k >> 1;
+  const uint32_t q = 2u * j + (b >> 1), pos = 2u * (b & 1u) + (k & 1u);
+  return 8u * pos + 4u * (q >> 2) + (q & 3u);
+}
+
+// One sample's 32 sites: lookups, column AND, is-N word, N count and block summary. Lanes past the
+// end of the alignment carry 'N' bytes and validp == 0, so every lane of a warp runs the same code.
+// The summary byte is only computed and stored when the warp saw an N at all (the buffer is pre-zeroed).
+__device__ __forceinline__ void pack_one_sample(const uint4 &a, const uint4 &b, uint32_t *np, uint8_t *sp, uint32_t *cnt,
+                                                const uint8_t *slut, uint32_t (&acc)[8], uint32_t validp, uint32_t lane) {
+  uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
+  pack_unit<0, 1>(a.x, a.y, slut, m0, m1);
+  pack_unit<2, 3>(a.z, a.w, slut, m2, m3);
+  pack_unit<0, 1>(b.x, b.y, slut, m4, m5);
+  pack_unit<2, 3>(b.z, b.w, slut, m6, m7);
+  acc[0] &= m0; acc[1] &= m1; acc[2] &= m2; acc[3] &= m3;
+  acc[4] &= m4; acc[5] &= m5; acc[6] &= m6; acc[7] &= m7;
+  // the four flag positions of a half are disjoint: OR them, then interleave the two halves
+  const uint32_t f0 = m0 | m1 | m2 | m3, f1 = m4 | m5 | m6 | m7;
+  const uint32_t isn = bsel(f1, f0 >> 4, 0xF0F0F0F0u) & validp;
+  __stcs(np, isn);
+  const uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
+  if (nz) {
+    const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, __popc(isn));
+    if (lane == 0) {
+      atomicAdd(cnt, wsum);
+      // block summary: one bit per 4 words (128 sites), one byte per warp (1024 sites)
+      uint32_t t2 = nz | (nz >> 1);
+      t2 |= (t2 >> 2);
+      t2 &= 0x11111111u;
+      *sp = (uint8_t)nibbles_all_ones(t2 * 0xFu);
+    }
+  }
+}
+
+// `rows` consecutive samples of one 32-site word. Running pointers (no 64-bit index arithmetic per sample);
+// PACK_BATCH samples per trip: all global loads of the batch are issued before any lookup, so every thread
+// keeps 2 * PACK_BATCH 16-byte loads in flight. STREAM: evict-first loads (single pass over the bytes).
+template <bool STREAM>
+__device__ __forceinline__ void pack_rows(const uint8_t *src, uint64_t pitch, uint32_t rows, bool has_sites, uint32_t *np,
+                                          uint64_t npitch, uint8_t *sp, uint64_t spitch, uint32_t *cnt, const uint8_t *slut,
+                                          uint32_t (&acc)[8], uint32_t validp, uint32_t lane) {
+  const uint4 kN = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);  // 'N': neutral for the column AND
+  auto load = [](const uint4 *p) { return STREAM ? __ldcs(p) : __ldcg(p); };
+  uint32_t r = 0;
+  for (; r + PACK_BATCH <= rows; r += PACK_BATCH) {
+    uint4 va[PACK_BATCH], vb[PACK_BATCH];
+#pragma unroll
+    for (int t = 0; t < PACK_BATCH; ++t) {
+      if (has_sites) {
+        va[t] = load(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch));
+        vb[t] = load(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch) + 1);
+      } else {
+        va[t] = vb[t] = kN;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < PACK_BATCH; ++t)
+      pack_one_sample(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, slut, acc, validp, lane);
+    src += (size_t)PACK_BATCH * pitch;
+    np += (size_t)PACK_BATCH * npitch;
+    sp += (size_t)PACK_BATCH * spitch;
+    cnt += PACK_BATCH;
+  }
+  for (; r < rows; ++r) {  // tail
+    uint4 va = kN, vb = kN;
+    if (has_sites) {
+      va = load(reinterpret_cast<const uint4 *>(src));
+      vb = load(reinterpret_cast<const uint4 *>(src) + 1);
+    }
+    pack_one_sample(va, vb, np, sp, cnt, slut, acc, validp, lane);
+    src += pitch; np += npitch; sp += spitch; ++cnt;
+  }
+}
+
+// valid sites of a word, in N-plane bit order
+__device__ __forceinline__ uint32_t pack_validp(uint32_t nvalid) {
+  uint32_t validp = nvalid == 32u ? 0xFFFFFFFFu : 0u;
+  if (nvalid > 0u && nvalid < 32u)
+    for (uint32_t t = 0; t < nvalid; ++t) validp |= 1u << pack_nbit(t);
+  return validp;
+}
+
+// column-AND word of sites 8j..8j+7 (site-ordered nibbles) from the byte-per-site accumulators
+__device__ __forceinline__ uint32_t pack_colword(const uint32_t (&acc)[8], int j, uint32_t nvalid) {
+  // acc[2j] holds sites (0, 4, 1, 5) of the group, acc[2j+1] sites (2, 6, 3, 7), one per byte
+  const uint32_t A = acc[2 * j], B = acc[2 * j + 1];
+  uint32_t cw = (A & 0xFu) | (((A >> 16) & 0xFu) << 4) | ((B & 0xFu) << 8) | (((B >> 16) & 0xFu) << 12) |
+                (((A >> 8) & 0xFu) << 16) | (((A >> 24) & 0xFu) << 20) | (((B >> 8) & 0xFu) << 24) | (((B >> 24) & 0xFu) << 28);
+  // sites >= L in the last word must not look variable: force their nibbles non-zero
+  const uint32_t v = nvalid > (uint32_t)j * 8u ? min(8u, nvalid - (uint32_t)j * 8u) : 0u;
+  if (v < 8u) cw |= (v == 0u ? 0xFFFFFFFFu : (0xFFFFFFFFu << (4u * v)));
+  return cw;
+}
+
 __global__ void __launch_bounds__(PACK_THREADS)
 k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
        uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/,
        uint32_t *__restrict__ ncount) {
-  extern __shared__ __align__(256) char lut[];
-  __shared__ uint32_t s_ncnt[PACK_SCHUNK];  // N count of this CTA's 16 K sites, per sample of the chunk
+  __shared__ uint8_t slut[256];
+  __shared__ uint32_t s_ncnt[PACK_SCHUNK];  // N count of this CTA's sites, per sample of the chunk
   for (int i = threadIdx.x; i < PACK_SCHUNK; i += PACK_THREADS) s_ncnt[i] = 0;
-  for (int i = threadIdx.x; i < 256 * 32; i += PACK_THREADS) {
-    const uint32_t m = base_mask(i >> 5);
-    *reinterpret_cast<uint32_t *>(lut + ((i >> 5) << 8) + ((i & 31) << 2)) = m * 0x1111u | (m == 15u ? 0xFFFF0000u : 0u);
-  }
+  for (int i = threadIdx.x; i < 256; i += PACK_THREADS) slut[i] = (uint8_t)base_mask(i);
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t lane4 = lane << 2;
   const uint64_t w = (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x;  // word index
   const uint64_t s0 = (uint64_t)blockIdx.y * PACK_SCHUNK;
   const uint64_t s1 = min(n, s0 + PACK_SCHUNK);
@@ -109,94 +244,24 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch,
   // npitch is a multiple of 32 words, so a whole warp is either inside or outside the N-plane row
   const bool in_row = w < npitch;
   const bool has_sites = site0 < L;
-  uint32_t acc0 = ~0u, acc1 = ~0u, acc2 = ~0u, acc3 = ~0u;
-  uint32_t valid = has_sites ? 0xFFFFFFFFu : 0u;
-  if (has_sites && L - site0 < 32) valid = (1u << (uint32_t)(L - site0)) - 1u;
-  // One sample's 32 sites: table lookups, column AND, is-N word, N count and block summary. Lanes past the
-  // end of the alignment carry 'N' bytes and valid == 0, so every lane of a warp runs the same code.
-  // Running pointers (no 64-bit index arithmetic per sample); the summary byte is only computed and stored
-  // when the warp saw an N at all (the buffer is pre-zeroed).
-  auto one_sample = [&](const uint4 &a, const uint4 &b, uint32_t *np, uint8_t *sp, uint32_t *cnt) {
-    const uint32_t x0 = lut4(lut, lane4, a.x), x1 = lut4(lut, lane4, a.y), x2 = lut4(lut, lane4, a.z), x3 = lut4(lut, lane4, a.w);
-    const uint32_t x4 = lut4(lut, lane4, b.x), x5 = lut4(lut, lane4, b.y), x6 = lut4(lut, lane4, b.z), x7 = lut4(lut, lane4, b.w);
-    // eight sites per register: 4-bit masks
-    acc0 &= __byte_perm(x0, x1, 0x5410);
-    acc1 &= __byte_perm(x2, x3, 0x5410);
-    acc2 &= __byte_perm(x4, x5, 0x5410);
-    acc3 &= __byte_perm(x6, x7, 0x5410);
-    // byte 2 of each pair: is-N flags of eight sites
-    const uint32_t n0 = bsel(x0, x1, 0x000F0000u), n1 = bsel(x2, x3, 0x000F0000u);
-    const uint32_t n2 = bsel(x4, x5, 0x000F0000u), n3 = bsel(x6, x7, 0x000F0000u);
-    const uint32_t isn = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n2, n3, 0x0062), 0x5410) & valid;
-    __stcs(np, isn);
-    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
-    if (nz) {
-      const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, __popc(isn));
-      if (lane == 0) {
-        atomicAdd(cnt, wsum);
-        // block summary: one bit per 4 words (128 sites), one byte per warp (1024 sites)
-        uint32_t t2 = nz | (nz >> 1);
-        t2 |= (t2 >> 2);
-        t2 &= 0x11111111u;
-        *sp = (uint8_t)nibbles_all_ones(t2 * 0xFu);
-      }
-    }
-  };
-  const uint4 kN = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);  // 'N': neutral for the column AND
-  if (in_row) {  // warp-uniform: npitch is a multiple of 32 words
-    const uint8_t *src = seqs + s0 * pitch + (has_sites ? site0 : 0);
-    uint32_t *np = nplane + s0 * npitch + w;
-    uint8_t *sp = nsum + s0 * spitch + (w >> 5);
-    uint32_t *cnt = s_ncnt;
-    uint64_t sb = s0;
-    // PACK_BATCH samples per trip: all global loads of the batch are issued before any table lookup,
-    // so every thread keeps 2 * PACK_BATCH 16-byte loads in flight
-    for (; sb + PACK_BATCH <= s1; sb += PACK_BATCH) {
-      uint4 va[PACK_BATCH], vb[PACK_BATCH];
+  uint32_t acc[8];
 #pragma unroll
-      for (int t = 0; t < PACK_BATCH; ++t) {
-        if (has_sites) {
-          va[t] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch));
-          vb[t] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch) + 1);
-        } else {
-          va[t] = vb[t] = kN;
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < PACK_BATCH; ++t) one_sample(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t);
-      src += (size_t)PACK_BATCH * pitch;
-      np += (size_t)PACK_BATCH * npitch;
-      sp += (size_t)PACK_BATCH * spitch;
-      cnt += PACK_BATCH;
-    }
-    for (; sb < s1; ++sb) {  // tail of the chunk
-      uint4 va = kN, vb = kN;
-      if (has_sites) {
-        va = __ldcs(reinterpret_cast<const uint4 *>(src));
-        vb = __ldcs(reinterpret_cast<const uint4 *>(src) + 1);
-      }
-      one_sample(va, vb, np, sp, cnt);
-      src += pitch; np += npitch; sp += spitch; ++cnt;
-    }
-  }
+  for (int q = 0; q < 8; ++q) acc[q] = ~0u;
+  const uint32_t nvalid = has_sites ? (uint32_t)min((uint64_t)32, L - site0) : 0u;
+  const uint32_t validp = pack_validp(nvalid);
+  if (in_row)  // warp-uniform
+    pack_rows<true>(seqs + s0 * pitch + (has_sites ? site0 : 0), pitch, (uint32_t)(s1 - s0), has_sites, nplane + s0 * npitch + w,
+                    npitch, nsum + s0 * spitch + (w >> 5), spitch, s_ncnt, slut, acc, validp, lane);
   __syncthreads();
   for (uint64_t i = threadIdx.x; i < s1 - s0; i += PACK_THREADS)
     if (s_ncnt[i]) atomicAdd(ncount + s0 + i, s_ncnt[i]);
   if (has_sites) {
-    // sites >= L in the last word must not look variable: force their nibbles non-zero
-    if (valid != 0xFFFFFFFFu) {
-      uint32_t nv = __popc(valid);
-      auto fix = [&](uint32_t &acc, uint32_t g) {
-        uint32_t v = nv > g * 8 ? min(8u, nv - g * 8) : 0u;
-        if (v < 8) acc |= (v == 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (4 * v)));
-      };
-      fix(acc0, 0); fix(acc1, 1); fix(acc2, 2); fix(acc3, 3);
-    }
     uint32_t *cm = colmask + w * 4;
-    if (acc0 != ~0u) atomicAnd(cm + 0, acc0);
-    if (acc1 != ~0u) atomicAnd(cm + 1, acc1);
-    if (acc2 != ~0u) atomicAnd(cm + 2, acc2);
-    if (acc3 != ~0u) atomicAnd(cm + 3, acc3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t cw = pack_colword(acc, j, nvalid);
+      if (cw != ~0u) atomicAnd(cm + j, cw);
+    }
   }
 }
 
@@ -698,6 +763,7 @@ __global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t
 
 }  // namespace tracs
 #include "sweep_tc.inl"
+#include "ingest_fused.inl"
 namespace tracs {
 
 // One launch of the tile sweep over a.n_tiles tiles and a.Wp words: tensor-core kernel when the masks
@@ -742,6 +808,54 @@ struct Ingested {
   bool partial_ambiguity = false;      // some variable site carries a 2- or 3-base IUPAC code
 };
 
+// Geometry of the single-pass ingest: strip width, items per strip, samples per item.
+struct IngestPlan {
+  bool fused = false;
+  uint32_t sw = 0, n_strips = 0, n_items = 0, chunk = 0, resident = 0;
+};
+static IngestPlan plan_ingest(uint64_t n, uint64_t L) {
+  IngestPlan p;
+  // TRACS_INGEST=split forces the two-kernel path, =fused the single-pass one whenever it is possible at all
+  // (TRACS_INGEST_SW pins the strip width in words; both are read per call so that tests can switch them)
+  const char *e = getenv("TRACS_INGEST");
+  const int mode = !e ? 0 : (!strcmp(e, "split") ? 1 : (!strcmp(e, "fused") ? 2 : 0));
+  if (mode != 2 || n == 0 || L == 0 || L >= (1ull << 32)) return p;  // opt-in until it beats the two-kernel path
+  static int n_sm = 0, occ = 0;
+  static size_t l2 = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    TRACS_CK(cudaGetDevice(&dev));
+    TRACS_CK(cudaGetDeviceProperties(&prop, dev));
+    TRACS_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ingest, ING_THREADS, 0));
+    l2 = (size_t)prop.l2CacheSize;
+    n_sm = prop.multiProcessorCount;
+  }
+  if (occ < 1) return p;
+  // three strips of sw words x n samples must fit in half of L2
+  uint32_t sw = ING_SW_MAX;
+  while (sw >= 32 && 3ull * n * sw * 32 > l2 / 2) sw >>= 1;
+  if (sw < 32) {
+    if (mode != 2) return p;
+    sw = 32;
+  }
+  if (const char *f = getenv("TRACS_INGEST_SW")) {
+    const int v = atoi(f);
+    if (v == 32 || v == 64 || v == 128 || v == 256) sw = (uint32_t)v;
+  }
+  const uint32_t subs = ING_THREADS / sw;
+  uint64_t chunk = round_up(std::max<uint64_t>(1, (n + n_sm - 1) / n_sm), subs);
+  chunk = std::min<uint64_t>(chunk, ING_CHUNK_MAX);
+  const uint64_t n_items = (n + chunk - 1) / chunk;
+  const uint64_t resident = (uint64_t)n_sm * occ;
+  const uint64_t n_strips = (L + (uint64_t)sw * 32 - 1) / ((uint64_t)sw * 32);
+  if (n_items > resident / 2 || n_strips * n_items >= (1ull << 32)) return p;  // every wait must be on a running CTA
+  p.fused = true;
+  p.sw = sw; p.chunk = (uint32_t)chunk; p.n_items = (uint32_t)n_items; p.n_strips = (uint32_t)n_strips;
+  p.resident = (uint32_t)resident;
+  return p;
+}
+
 // ASCII matrix (device) -> N-plane + summaries + variable-site bit-planes (K0a + K0b)
 static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, bool want_n, bool keep_site_idx,
                           Ingested &g, cudaStream_t st) {
@@ -759,34 +873,85 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   DevBuf<uint32_t> colmask(std::max<uint64_t>(1, Lw * 4));
   DevBuf<uint32_t> &nplane = g.nplane, &ncount = g.ncount;
   DevBuf<uint8_t> &nsum = g.nsum;
-  // N-plane is always produced by k_pack (same pass over the ASCII bytes)
+  // N-plane is always produced by the pack pass (same pass over the ASCII bytes)
   nplane.alloc(n * npitch);
   nsum.alloc(n * spitch);
   ncount.alloc(n);
+  const uint32_t Npad = (uint32_t)round_up(n, TILE);
+  DevBuf<uint32_t> &site_idx = g.site_idx;
   T.start();
   TRACS_CK(cudaMemsetAsync(colmask.p, 0xFF, colmask.n * sizeof(uint32_t), st));
   TRACS_CK(cudaMemsetAsync(nsum.p, 0, nsum.n, st));
-  if (L > 0) {
-    dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((n + PACK_SCHUNK - 1) / PACK_SCHUNK));
-    static bool pack_attr = false;
-    if (!pack_attr) {
-      TRACS_CK(cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PACK_SMEM));
-      pack_attr = true;
-    }
-    TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
-    k_pack<<<grid, PACK_THREADS, PACK_SMEM, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p);
+  TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
+
+  // ---- single-pass ingest (ingest_fused.inl) when three strips of the alignment fit in L2 ----------------
+  const IngestPlan ip = plan_ingest(n, L);
+  bool fused_done = false;
+  if (ip.fused) {
+    const uint64_t cap_sites = std::min<uint64_t>(round_up(L, 32), std::max<uint64_t>(65536, round_up(L / 8, 32)));
+    site_idx.alloc(cap_sites);
+    g.planes.alloc((size_t)(cap_sites / 32 + KC) * Npad);
+    // done[n_strips] ready[n_strips] base[n_strips + 1] flags[2] next[1]
+    DevBuf<uint32_t> sync((size_t)ip.n_strips * 3 + 4);
+    TRACS_CK(cudaMemsetAsync(sync.p, 0, sync.n * sizeof(uint32_t), st));
+    IngestArgs a;
+    a.seqs = dev_seqs; a.n = n; a.L = L; a.pitch = pitch;
+    a.colmask = colmask.p; a.nplane = nplane.p; a.npitch = npitch; a.nsum = nsum.p; a.spitch = spitch; a.ncount = ncount.p;
+    a.sw = ip.sw; a.n_strips = ip.n_strips; a.n_items = ip.n_items; a.chunk = ip.chunk;
+    a.done = sync.p; a.ready = sync.p + ip.n_strips; a.base = sync.p + 2 * (size_t)ip.n_strips;
+    a.flags = a.base + ip.n_strips + 1; a.next = a.flags + 2;
+    a.site_idx = site_idx.p; a.cap_sites = (uint32_t)cap_sites; a.planes = g.planes.p; a.Npad = Npad;
+    const uint64_t total_items = (uint64_t)ip.n_strips * ip.n_items;
+    k_ingest<<<(unsigned)std::min<uint64_t>(ip.resident, total_items), ING_THREADS, 0, st>>>(a);
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
-  } else {
+    S.ms_pack += T.stop();
+    T.start();
+    uint32_t h[3] = {0, 0, 0};  // V, ambiguity, overflow
+    TRACS_CK(cudaMemcpyAsync(&h[0], a.base + ip.n_strips, 4, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(&h[1], a.flags, 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaStreamSynchronize(st));
+    if (!h[2]) {
+      const uint64_t V = h[0];
+      const uint64_t W = (V + 31) / 32;
+      const uint32_t Wp = (uint32_t)std::max<uint64_t>(KC, round_up(W, KC));
+      g.V = V; g.W = W; g.Wp = Wp; g.Npad = Npad;
+      S.n_variable_sites += V;
+      S.n_words += Wp;
+      g.partial_ambiguity = h[1] != 0;
+      // neutral padding: plane words W..Wp and samples n..Npad of every word
+      if (Wp > W) TRACS_CK(cudaMemsetAsync(g.planes.p + (size_t)W * Npad, 0xFF, (size_t)(Wp - W) * Npad * sizeof(uint4), st));
+      if (Npad > n && W > 0)
+        TRACS_CK(cudaMemset2DAsync(g.planes.p + n, (size_t)Npad * sizeof(uint4), 0xFF, (size_t)(Npad - n) * sizeof(uint4), W, st));
+      g.planesT.alloc((size_t)Wp * n);
+      dim3 tg((unsigned)((n + 31) / 32), (unsigned)((Wp + 31) / 32));
+      k_planes_transpose<<<tg, 256, 0, st>>>(g.planes.p, Npad, n, Wp, g.planesT.p);
+      S.kernel_launches++;
+      TRACS_CK(cudaGetLastError());
+      S.ms_compact += T.stop();
+      if (!keep_site_idx) site_idx.release();
+      return;
+    }
+    // more variable sites than the planes were sized for: the column AND, N-plane and counts are complete,
+    // fall through to the two-pass selection + gather
+    fused_done = true;
+    g.planes.release();
+    site_idx.release();
+    T.start();
+  }
+  if (L > 0 && !fused_done) {
+    dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((n + PACK_SCHUNK - 1) / PACK_SCHUNK));
+    k_pack<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p);
+    S.kernel_launches++;
+    TRACS_CK(cudaGetLastError());
+  } else if (L == 0) {
     TRACS_CK(cudaMemsetAsync(nplane.p, 0, nplane.n * sizeof(uint32_t), st));
-    TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
   }
   S.ms_pack += T.stop();
 
   // ---- K0b: variable sites -> planes -----------------------------------------------------
   T.start();
   uint64_t V = 0;
-  DevBuf<uint32_t> &site_idx = g.site_idx;
   if (L > 0) {
     DevBuf<uint8_t> flags(round_up(L, 8));
     k_siteflags<<<(unsigned)((Lw * 4 + 255) / 256), 256, 0, st>>>(colmask.p, L, flags.p);
@@ -804,7 +969,6 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   }
   const uint64_t W = (V + 31) / 32;
   const uint32_t Wp = (uint32_t)std::max<uint64_t>(KC, round_up(W, KC));
-  const uint32_t Npad = (uint32_t)round_up(n, TILE);
   g.V = V; g.W = W; g.Wp = Wp; g.Npad = Npad;
   S.n_variable_sites += V;
   S.n_words += Wp;
