@@ -44,32 +44,6 @@ def test_every_byte_value(oracle_mod):
     _cmp(tracs_b200.pairsnp_matrix(t, dist=IMAX), oracle_mod.pairsnp_ascii(t, dist=IMAX, n_threads=4))
 
 
-@pytest.mark.parametrize("sw", ["32", "64", "128", "256"])
-@pytest.mark.parametrize("n,L", [(300, 20000), (70, 70001), (1100, 9000)])
-def test_single_pass_ingest_matches_oracle(oracle_mod, monkeypatch, sw, n, L):
-    """k_ingest (strip-wise pack + in-L2 gather) at every strip width, forced on small inputs."""
-    s = synth.generate(n, L, p_var=0.05, n_clusters=4, mu=3, p_N=0.02, p_amb=0.05, seed=n + L, lowercase=0.05,
-                       odd_chars=0.01, three_base=True)
-    orc = oracle_mod.pairsnp_ascii(s, dist=IMAX if n < 1000 else 40, n_threads=4)
-    monkeypatch.setenv("TRACS_INGEST", "fused")
-    monkeypatch.setenv("TRACS_INGEST_SW", sw)
-    res = tracs_b200.pairsnp_matrix(s, dist=IMAX if n < 1000 else 40)
-    assert tracs_b200.last_stats()["kernel_launches"] > 0
-    _cmp(res, orc)
-    monkeypatch.setenv("TRACS_INGEST", "split")
-    _cmp(tracs_b200.pairsnp_matrix(s, dist=IMAX if n < 1000 else 40), orc)
-
-
-def test_single_pass_ingest_overflow_falls_back(oracle_mod, monkeypatch):
-    """More variable sites than the planes were sized for: the two-pass selection takes over."""
-    rng = np.random.default_rng(3)
-    s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(40, 600_000))]
-    monkeypatch.setenv("TRACS_INGEST", "fused")
-    res = tracs_b200.pairsnp_matrix(s, dist=IMAX)
-    assert tracs_b200.last_stats()["n_variable_sites"] > 500_000
-    _cmp(res, oracle_mod.pairsnp_ascii(s, dist=IMAX, n_threads=4))
-
-
 @pytest.mark.parametrize("n_clusters,dist,expect", [(60, 20, "refine"), (3, 20, "fallback"), (60, 0, "refine"), (3, 2047, "any")])
 def test_prefilter_refine_and_fallback(oracle_mod, n_clusters, dist, expect):
     # long enough (>= 256 words of variable sites) for the filter-and-refine path to engage

@@ -763,7 +763,6 @@ __global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t
 
 }  // namespace tracs
 #include "sweep_tc.inl"
-#include "ingest_fused.inl"
 namespace tracs {
 
 // One launch of the tile sweep over a.n_tiles tiles and a.Wp words: tensor-core kernel when the masks
@@ -808,54 +807,6 @@ struct Ingested {
   bool partial_ambiguity = false;      // some variable site carries a 2- or 3-base IUPAC code
 };
 
-// Geometry of the single-pass ingest: strip width, items per strip, samples per item.
-struct IngestPlan {
-  bool fused = false;
-  uint32_t sw = 0, n_strips = 0, n_items = 0, chunk = 0, resident = 0;
-};
-static IngestPlan plan_ingest(uint64_t n, uint64_t L) {
-  IngestPlan p;
-  // TRACS_INGEST=split forces the two-kernel path, =fused the single-pass one whenever it is possible at all
-  // (TRACS_INGEST_SW pins the strip width in words; both are read per call so that tests can switch them)
-  const char *e = getenv("TRACS_INGEST");
-  const int mode = !e ? 0 : (!strcmp(e, "split") ? 1 : (!strcmp(e, "fused") ? 2 : 0));
-  if (mode != 2 || n == 0 || L == 0 || L >= (1ull << 32)) return p;  // opt-in until it beats the two-kernel path
-  static int n_sm = 0, occ = 0;
-  static size_t l2 = 0;
-  if (!n_sm) {
-    int dev = 0;
-    cudaDeviceProp prop;
-    TRACS_CK(cudaGetDevice(&dev));
-    TRACS_CK(cudaGetDeviceProperties(&prop, dev));
-    TRACS_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ingest, ING_THREADS, 0));
-    l2 = (size_t)prop.l2CacheSize;
-    n_sm = prop.multiProcessorCount;
-  }
-  if (occ < 1) return p;
-  // three strips of sw words x n samples must fit in half of L2
-  uint32_t sw = ING_SW_MAX;
-  while (sw >= 32 && 3ull * n * sw * 32 > l2 / 2) sw >>= 1;
-  if (sw < 32) {
-    if (mode != 2) return p;
-    sw = 32;
-  }
-  if (const char *f = getenv("TRACS_INGEST_SW")) {
-    const int v = atoi(f);
-    if (v == 32 || v == 64 || v == 128 || v == 256) sw = (uint32_t)v;
-  }
-  const uint32_t subs = ING_THREADS / sw;
-  uint64_t chunk = round_up(std::max<uint64_t>(1, (n + n_sm - 1) / n_sm), subs);
-  chunk = std::min<uint64_t>(chunk, ING_CHUNK_MAX);
-  const uint64_t n_items = (n + chunk - 1) / chunk;
-  const uint64_t resident = (uint64_t)n_sm * occ;
-  const uint64_t n_strips = (L + (uint64_t)sw * 32 - 1) / ((uint64_t)sw * 32);
-  if (n_items > resident / 2 || n_strips * n_items >= (1ull << 32)) return p;  // every wait must be on a running CTA
-  p.fused = true;
-  p.sw = sw; p.chunk = (uint32_t)chunk; p.n_items = (uint32_t)n_items; p.n_strips = (uint32_t)n_strips;
-  p.resident = (uint32_t)resident;
-  return p;
-}
-
 // ASCII matrix (device) -> N-plane + summaries + variable-site bit-planes (K0a + K0b)
 static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, bool want_n, bool keep_site_idx,
                           Ingested &g, cudaStream_t st) {
@@ -884,67 +835,12 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   TRACS_CK(cudaMemsetAsync(nsum.p, 0, nsum.n, st));
   TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
 
-  // ---- single-pass ingest (ingest_fused.inl) when three strips of the alignment fit in L2 ----------------
-  const IngestPlan ip = plan_ingest(n, L);
-  bool fused_done = false;
-  if (ip.fused) {
-    const uint64_t cap_sites = std::min<uint64_t>(round_up(L, 32), std::max<uint64_t>(65536, round_up(L / 8, 32)));
-    site_idx.alloc(cap_sites);
-    g.planes.alloc((size_t)(cap_sites / 32 + KC) * Npad);
-    // done[n_strips] ready[n_strips] base[n_strips + 1] flags[2] next[1]
-    DevBuf<uint32_t> sync((size_t)ip.n_strips * 3 + 4);
-    TRACS_CK(cudaMemsetAsync(sync.p, 0, sync.n * sizeof(uint32_t), st));
-    IngestArgs a;
-    a.seqs = dev_seqs; a.n = n; a.L = L; a.pitch = pitch;
-    a.colmask = colmask.p; a.nplane = nplane.p; a.npitch = npitch; a.nsum = nsum.p; a.spitch = spitch; a.ncount = ncount.p;
-    a.sw = ip.sw; a.n_strips = ip.n_strips; a.n_items = ip.n_items; a.chunk = ip.chunk;
-    a.done = sync.p; a.ready = sync.p + ip.n_strips; a.base = sync.p + 2 * (size_t)ip.n_strips;
-    a.flags = a.base + ip.n_strips + 1; a.next = a.flags + 2;
-    a.site_idx = site_idx.p; a.cap_sites = (uint32_t)cap_sites; a.planes = g.planes.p; a.Npad = Npad;
-    const uint64_t total_items = (uint64_t)ip.n_strips * ip.n_items;
-    k_ingest<<<(unsigned)std::min<uint64_t>(ip.resident, total_items), ING_THREADS, 0, st>>>(a);
-    S.kernel_launches++;
-    TRACS_CK(cudaGetLastError());
-    S.ms_pack += T.stop();
-    T.start();
-    uint32_t h[3] = {0, 0, 0};  // V, ambiguity, overflow
-    TRACS_CK(cudaMemcpyAsync(&h[0], a.base + ip.n_strips, 4, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaMemcpyAsync(&h[1], a.flags, 8, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaStreamSynchronize(st));
-    if (!h[2]) {
-      const uint64_t V = h[0];
-      const uint64_t W = (V + 31) / 32;
-      const uint32_t Wp = (uint32_t)std::max<uint64_t>(KC, round_up(W, KC));
-      g.V = V; g.W = W; g.Wp = Wp; g.Npad = Npad;
-      S.n_variable_sites += V;
-      S.n_words += Wp;
-      g.partial_ambiguity = h[1] != 0;
-      // neutral padding: plane words W..Wp and samples n..Npad of every word
-      if (Wp > W) TRACS_CK(cudaMemsetAsync(g.planes.p + (size_t)W * Npad, 0xFF, (size_t)(Wp - W) * Npad * sizeof(uint4), st));
-      if (Npad > n && W > 0)
-        TRACS_CK(cudaMemset2DAsync(g.planes.p + n, (size_t)Npad * sizeof(uint4), 0xFF, (size_t)(Npad - n) * sizeof(uint4), W, st));
-      g.planesT.alloc((size_t)Wp * n);
-      dim3 tg((unsigned)((n + 31) / 32), (unsigned)((Wp + 31) / 32));
-      k_planes_transpose<<<tg, 256, 0, st>>>(g.planes.p, Npad, n, Wp, g.planesT.p);
-      S.kernel_launches++;
-      TRACS_CK(cudaGetLastError());
-      S.ms_compact += T.stop();
-      if (!keep_site_idx) site_idx.release();
-      return;
-    }
-    // more variable sites than the planes were sized for: the column AND, N-plane and counts are complete,
-    // fall through to the two-pass selection + gather
-    fused_done = true;
-    g.planes.release();
-    site_idx.release();
-    T.start();
-  }
-  if (L > 0 && !fused_done) {
+  if (L > 0) {
     dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((n + PACK_SCHUNK - 1) / PACK_SCHUNK));
     k_pack<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p);
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
-  } else if (L == 0) {
+  } else {
     TRACS_CK(cudaMemsetAsync(nplane.p, 0, nplane.n * sizeof(uint32_t), st));
   }
   S.ms_pack += T.stop();
