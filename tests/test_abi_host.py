@@ -149,6 +149,57 @@ def test_fasta_loader_large_roundtrip(tmp_path):
         assert names == ["s%d" % i for i in range(50)] and np.array_equal(a, s)
 
 
+def _read_both(p):
+    """(sequential result or error text, 4-thread result or error text) of the loader on one file."""
+    out = []
+    for nt in (1, 4):
+        try:
+            a, names = tracs_b200.read_fasta(p, n_threads=nt)
+            out.append((names, a.shape, a.tobytes()))
+        except RuntimeError as e:
+            out.append(str(e))
+    return out
+
+
+def test_fasta_loader_threads_equal_sequential(tmp_path, monkeypatch):
+    # the multi-threaded reader of plain files must be indistinguishable from the sequential state machine:
+    # same names, order, bases -- and the same error -- also where it has to hand the file back
+    monkeypatch.setenv("TRACS_FASTA_PAR_MIN", "0")
+    cases = {
+        "plain": b">a desc here\nACGT\nAC\n>b\nAC-NNT\n>c\nACGTAC\n",
+        "crlf": b">a\tx\r\nAC GT\r\n\r\nAC\r\n>b\r\nACGTAC\r\n>c x\r\nACGTAC",
+        "junk_first": b"junk line\n>a\nACGT\n>b\nACGA\n",
+        "gt_in_header": b">a > b >c\nACGT\n>b>x\nACGA\n>c\nAAAA\n",
+        "gt_inside_seq": b">a\nACGT\n>b\nAC>x\nGT\n>c\nACGT\n",
+        "at_inside_seq": b">a\nACGT\n>b\nAC@x\nGT\n>c\nACGT\n",
+        "plus_inside_seq": b">a\nACGT\n>b\nACGT\n+\nIIII\n>c\nACGT\n",
+        "fastq": b"@r1 d\nACGT\n+\nIIII\n@r2\nACGA\n+r2\nII!I\n",
+        "fastq_after_fasta": b">a\nACGT\n>b\nACGT\n@r\nACGA\n+\nIIII\n",
+        "empty_seqs": b">a\n>b\n>c\n",
+        "last_header_only": b">a\nACGT\n>b\nACGT\n>c",
+        "last_gt_only": b">a\nACGT\n>b\nACGT\n>",
+        "last_no_newline": b">a\nACGT\n>b\nACGT\n>c\nACGA",
+        "ragged_middle": b">a\nACGT\n>b\nACG\n>c\nACGT\n",
+        "ragged_last": b">a\nACGT\n>b\nACGT\n>c\nACG\n",
+        "ragged_long": b">a\nACGT\n>b\nACGTACGTACGTACGTACGTACGTACGTACGTAAA\n>c\nACGT\n",
+        "ragged_then_truncated_fastq": b">a\nACGT\n>b\nACG\n@c\nACGT\n+\nII",
+        "truncated_fastq_tail": b">a\nACGT\n>b\nACGT\n@c\nACGT\n+\nII",
+        "blank_lines": b">a\n\n\nAC\n\nGT\n\n>b\n\nACGT\n\n\n>c\nACGT\n\n",
+        "long_lines": b"".join(b">s%d\n" % i + b"ACGTNacgtn-" * 37 + b"\n" + b"MRWSYKVHDB" * 11 + b"\n" for i in range(9)),
+    }
+    for tag, data in cases.items():
+        p = str(tmp_path / (tag + ".fa"))
+        open(p, "wb").write(data)
+        seq, par = _read_both(p)
+        assert seq == par, tag
+    s = synth.generate(64, 30011, p_var=0.02, seed=9, lowercase=0.05)
+    for width in (0, 61):
+        p = str(tmp_path / ("big%d.fa" % width))
+        synth.write_fasta(p, s, width=width, descriptions=True)
+        a, names = tracs_b200.read_fasta(p, n_threads=8)
+        assert names == ["s%d" % i for i in range(64)] and np.array_equal(a, s)
+
+
 def test_shard_dealing_covers_and_balances():
     for n_rb, world in ((1, 1), (7, 2), (79, 8), (782, 8), (5, 8), (16, 4)):
         parts = [tracs_b200.shard_rowblocks(n_rb, world, r) for r in range(world)]

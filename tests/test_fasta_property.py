@@ -44,6 +44,13 @@ def test_loader_matches_oracle_reader(oracle_mod, tmp_path_factory, data, gz):
     exp = oracle_mod.pairsnp([p], dist=2147483647)
     assert names == exp[3]
     assert a.shape == (n, L)
+    # the multi-threaded reader (plain files; forced on tiny inputs) must agree byte for byte
+    os.environ["TRACS_FASTA_PAR_MIN"] = "0"
+    try:
+        a4, names4 = tracs_b200.read_fasta(p, n_threads=4)
+    finally:
+        del os.environ["TRACS_FASTA_PAR_MIN"]
+    assert names4 == names and a4.shape == a.shape and np.array_equal(a4, a)
     if n >= 2 and L > 0:
         got = oracle_mod.pairsnp_ascii(a, dist=2147483647)
         assert got[2].tolist() == exp[2] and got[4].tolist() == exp[5]
