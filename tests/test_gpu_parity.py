@@ -44,6 +44,18 @@ def test_every_byte_value(oracle_mod):
     _cmp(tracs_b200.pairsnp_matrix(t, dist=IMAX), oracle_mod.pairsnp_ascii(t, dist=IMAX, n_threads=4))
 
 
+def test_pageable_source_is_staged(oracle_mod, monkeypatch):
+    """A large pageable host matrix goes through the multi-threaded staging copy: same result as the direct copy."""
+    s = synth.generate(600, 200_003, p_var=0.02, n_clusters=5, mu=3, p_N=0.01, seed=13)
+    monkeypatch.setenv("TRACS_H2D_STAGE_MIN", "0")
+    a = tracs_b200.pairsnp_matrix(s, dist=60)
+    monkeypatch.setenv("TRACS_H2D_STAGE_MIN", str(1 << 40))
+    b = tracs_b200.pairsnp_matrix(s, dist=60)
+    for k in ("rows", "cols", "dist", "ncomp"):
+        assert a[k].tolist() == b[k].tolist()
+    _cmp(a, oracle_mod.pairsnp_ascii(s, dist=60, n_threads=8))
+
+
 @pytest.mark.parametrize("n_clusters,dist,expect", [(60, 20, "refine"), (3, 20, "fallback"), (60, 0, "refine"), (3, 2047, "any")])
 def test_prefilter_refine_and_fallback(oracle_mod, n_clusters, dist, expect):
     # long enough (>= 256 words of variable sites) for the filter-and-refine path to engage

@@ -10,6 +10,8 @@
 #include <map>
 #include <mutex>
 #include <stdexcept>
+#include <string>
+#include <thread>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -377,6 +379,71 @@ static tracs_opts_t normalise(const tracs_opts_t *opts, size_t n) {
   return o;
 }
 
+// Host -> device copy of a row-major byte matrix. Page-locked sources go to the copy engine directly. A large
+// PAGEABLE source (numpy arrays, the FASTA reader's buffer) would be staged by the driver through one thread;
+// here a few workers copy row chunks into their own page-locked double buffers and queue each chunk on their
+// own stream, so the memcpy of one chunk overlaps the DMA of the others.
+static void h2d_rows(uint8_t *dev, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, size_t rows, cudaStream_t st) {
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  const char *env_min = getenv("TRACS_H2D_STAGE_MIN");  // read per call: tests switch it
+  const size_t min_bytes = env_min ? (size_t)strtoull(env_min, nullptr, 10) : ((size_t)256 << 20);
+  if (pinned || width * rows < min_bytes) {
+    TRACS_CK(cudaMemcpy2DAsync(dev, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  const size_t CH = (size_t)32 << 20;  // staging buffer
+  if (width > CH) {                    // very long rows: leave it to the driver
+    TRACS_CK(cudaMemcpy2DAsync(dev, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  TRACS_CK(cudaStreamSynchronize(st));  // work queued on `st` for the destination (padding fill) comes first
+  const char *env_thr = getenv("TRACS_H2D_THREADS");
+  const unsigned h2d_threads = env_thr ? (unsigned)std::max(1, atoi(env_thr)) : 12u;
+  const size_t rows_per = std::max<size_t>(1, CH / width);
+  const size_t n_chunks = (rows + rows_per - 1) / rows_per;
+  const int T = (int)std::min<size_t>(n_chunks, std::max(1u, std::min(h2d_threads, std::thread::hardware_concurrency())));
+  int devid = 0;
+  TRACS_CK(cudaGetDevice(&devid));
+  std::vector<std::string> errs((size_t)T);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < T; ++t)
+    pool.emplace_back([&, t] {
+      cudaStream_t ws = nullptr;
+      cudaEvent_t ev[2] = {nullptr, nullptr};
+      uint8_t *buf[2] = {nullptr, nullptr};
+      try {
+        TRACS_CK(cudaSetDevice(devid));
+        TRACS_CK(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+          buf[b] = (uint8_t *)host_pool_alloc(CH);
+          TRACS_CK(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+        }
+        int turn = 0;
+        for (size_t c = (size_t)t; c < n_chunks; c += (size_t)T, turn ^= 1) {
+          const size_t r0 = c * rows_per, nr = std::min(rows_per, rows - r0);
+          TRACS_CK(cudaEventSynchronize(ev[turn]));  // the DMA that last read this buffer is done
+          for (size_t r = 0; r < nr; ++r) memcpy(buf[turn] + r * width, src + (r0 + r) * spitch, width);
+          TRACS_CK(cudaMemcpy2DAsync(dev + r0 * dpitch, dpitch, buf[turn], width, width, nr, cudaMemcpyHostToDevice, ws));
+          TRACS_CK(cudaEventRecord(ev[turn], ws));
+        }
+        TRACS_CK(cudaStreamSynchronize(ws));
+      } catch (const std::exception &e) {
+        errs[t] = e.what();
+      }
+      for (int b = 0; b < 2; ++b) {
+        if (ev[b]) cudaEventDestroy(ev[b]);
+        if (buf[b]) host_pool_free(buf[b]);
+      }
+      if (ws) cudaStreamDestroy(ws);
+    });
+  for (auto &th : pool) th.join();
+  for (auto &e : errs)
+    if (!e.empty()) throw std::runtime_error("host to device staging: " + e);
+  (void)st;  // the workers have synchronised their streams: the data is in place for any stream
+}
+
 int tracs_pairsnp_device(const uint8_t *dev_seqs, size_t n, size_t L, size_t pitch, const tracs_opts_t *opts,
                          tracs_edges_t *out) {
   memset(out, 0, sizeof *out);
@@ -402,7 +469,7 @@ int tracs_pairsnp_host(const uint8_t *seqs, size_t n, size_t L, size_t pitch, co
       const size_t dp = std::max<size_t>(32, (L + 31) / 32 * 32);
       DevBuf<uint8_t> d(n * dp);
       if (dp != L) TRACS_CK(cudaMemsetAsync(d.p, 'N', n * dp, 0));
-      if (L > 0) TRACS_CK(cudaMemcpy2DAsync(d.p, dp, seqs, pitch, L, n, cudaMemcpyHostToDevice, 0));
+      if (L > 0) h2d_rows(d.p, dp, seqs, pitch, L, n, 0);
       sweep_device(d.p, n, L, dp, o, he, 0);
       g_stats.h2d_bytes += (uint64_t)n * L;
     }
