@@ -96,12 +96,15 @@ typedef struct tracs_opts {
 
 /* Replaces TRACS.pairsnp(fasta, n_threads, dist, filter) -- src/python_bindings.cpp:12-13,
  * src/pairsnp.hpp:320-458. paths: 1 or 2 FASTA(.gz) files (2 = query x db). n_threads sizes only
- * host-side parsing. */
+ * host-side parsing: a plain (uncompressed) file is parsed by n_threads workers whenever that is provably
+ * identical to the sequential kseq semantics (checked while parsing, else the sequential reader runs). */
 int tracs_pairsnp(const char *const *paths, int n_paths, int n_threads, int32_t dist, int filter,
                   tracs_edges_t *out);
 
 /* Same sweep on an alignment already held as an ASCII matrix seqs[n][pitch] (the bytes
- * load_seqs keeps per record, src/pairsnp.hpp:99-110) in HOST memory; includes the H2D copy. */
+ * load_seqs keeps per record, src/pairsnp.hpp:99-110) in HOST memory; includes the H2D copy
+ * (page-locked sources go to the copy engine directly; large pageable ones are staged by worker
+ * threads through page-locked double buffers). */
 int tracs_pairsnp_host(const uint8_t *seqs, size_t n, size_t L, size_t pitch, const tracs_opts_t *opts,
                        tracs_edges_t *out);
 
