@@ -56,6 +56,28 @@ def test_pageable_source_is_staged(oracle_mod, monkeypatch):
     _cmp(a, oracle_mod.pairsnp_ascii(s, dist=60, n_threads=8))
 
 
+@pytest.mark.parametrize("n,L,p_var", [(600, 20000, 0.03), (300, 70001, 0.02), (1100, 9000, 0.04), (257, 4096, 0.01), (900, 33000, 0.2)])
+def test_early_extraction_ingest_matches_oracle(oracle_mod, monkeypatch, n, L, p_var):
+    """k_pack with the extracting warp (sites listed from the first 256 samples) + late gather + k_slice must give
+    the planes of the two-pass ingest: forced on small inputs, compared with the oracle and with TRACS_INGEST=split."""
+    s = synth.generate(n, L, p_var=p_var, n_clusters=6, mu=3, p_N=0.02, p_amb=0.05, seed=n + L, lowercase=0.05,
+                       odd_chars=0.01, three_base=True)
+    # sites that only start to vary after the first chunk of samples
+    rng = np.random.default_rng(n)
+    for c in rng.integers(0, L, size=40):
+        s[:, c] = ord("A")
+        s[rng.integers(256, n), c] = ord("T")
+    dist = IMAX if n < 1000 else 60
+    orc = oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4)
+    monkeypatch.setenv("TRACS_INGEST", "early")
+    res = tracs_b200.pairsnp_matrix(s, dist=dist)
+    st_early = tracs_b200.last_stats()
+    _cmp(res, orc)
+    monkeypatch.setenv("TRACS_INGEST", "split")
+    _cmp(tracs_b200.pairsnp_matrix(s, dist=dist), orc)
+    assert tracs_b200.last_stats()["n_variable_sites"] == st_early["n_variable_sites"]
+
+
 @pytest.mark.parametrize("n_clusters,dist,expect", [(60, 20, "refine"), (3, 20, "fallback"), (60, 0, "refine"), (3, 2047, "any")])
 def test_prefilter_refine_and_fallback(oracle_mod, n_clusters, dist, expect):
     # long enough (>= 256 words of variable sites) for the filter-and-refine path to engage

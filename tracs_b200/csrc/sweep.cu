@@ -169,13 +169,12 @@ __device__ __forceinline__ void pack_one_sample(const uint4 &a, const uint4 &b, 
 
 // `rows` consecutive samples of one 32-site word. Running pointers (no 64-bit index arithmetic per sample);
 // PACK_BATCH samples per trip: all global loads of the batch are issued before any lookup, so every thread
-// keeps 2 * PACK_BATCH 16-byte loads in flight. STREAM: evict-first loads (single pass over the bytes).
-template <bool STREAM>
+// keeps 2 * PACK_BATCH 16-byte loads in flight (evict-first: a single pass over the bytes).
 __device__ __forceinline__ void pack_rows(const uint8_t *src, uint64_t pitch, uint32_t rows, bool has_sites, uint32_t *np,
                                           uint64_t npitch, uint8_t *sp, uint64_t spitch, uint32_t *cnt, const uint8_t *slut,
                                           uint32_t (&acc)[8], uint32_t validp, uint32_t lane) {
   const uint4 kN = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);  // 'N': neutral for the column AND
-  auto load = [](const uint4 *p) { return STREAM ? __ldcs(p) : __ldcg(p); };
+  auto load = [](const uint4 *p) { return __ldcs(p); };
   uint32_t r = 0;
   for (; r + PACK_BATCH <= rows; r += PACK_BATCH) {
     uint4 va[PACK_BATCH], vb[PACK_BATCH];
@@ -187,6 +186,10 @@ __device__ __forceinline__ void pack_rows(const uint8_t *src, uint64_t pitch, ui
       } else {
         va[t] = vb[t] = kN;
       }
+    }
+    if (has_sites && r + 2 * PACK_BATCH <= rows) {  // the next batch on its way into L2 while this one is handled
+#pragma unroll
+      for (int t = 0; t < PACK_BATCH; ++t) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(PACK_BATCH + t) * pitch));
     }
 #pragma unroll
     for (int t = 0; t < PACK_BATCH; ++t)
@@ -228,7 +231,7 @@ __device__ __forceinline__ uint32_t pack_colword(const uint32_t (&acc)[8], int j
 }
 
 __global__ void __launch_bounds__(PACK_THREADS)
-k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
+k_pack(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
        uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/,
        uint32_t *__restrict__ ncount) {
   __shared__ uint8_t slut[256];
@@ -238,8 +241,8 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch,
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t w = (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x;  // word index
-  const uint64_t s0 = (uint64_t)blockIdx.y * PACK_SCHUNK;
-  const uint64_t s1 = min(n, s0 + PACK_SCHUNK);
+  const uint64_t s0 = s_begin + (uint64_t)blockIdx.y * PACK_SCHUNK;
+  const uint64_t s1 = min(s_end, s0 + PACK_SCHUNK);
   const uint64_t site0 = w * 32;
   // npitch is a multiple of 32 words, so a whole warp is either inside or outside the N-plane row
   const bool in_row = w < npitch;
@@ -250,8 +253,135 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t L, uint64_t pitch,
   const uint32_t nvalid = has_sites ? (uint32_t)min((uint64_t)32, L - site0) : 0u;
   const uint32_t validp = pack_validp(nvalid);
   if (in_row)  // warp-uniform
-    pack_rows<true>(seqs + s0 * pitch + (has_sites ? site0 : 0), pitch, (uint32_t)(s1 - s0), has_sites, nplane + s0 * npitch + w,
-                    npitch, nsum + s0 * spitch + (w >> 5), spitch, s_ncnt, slut, acc, validp, lane);
+    pack_rows(seqs + s0 * pitch + (has_sites ? site0 : 0), pitch, (uint32_t)(s1 - s0), has_sites, nplane + s0 * npitch + w,
+              npitch, nsum + s0 * spitch + (w >> 5), spitch, s_ncnt, slut, acc, validp, lane);
+  __syncthreads();
+  for (uint64_t i = threadIdx.x; i < s1 - s0; i += PACK_THREADS)
+    if (s_ncnt[i]) atomicAdd(ncount + s0 + i, s_ncnt[i]);
+  if (has_sites) {
+    uint32_t *cm = colmask + w * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t cw = pack_colword(acc, j, nvalid);
+      if (cw != ~0u) atomicAnd(cm + j, cw);
+    }
+  }
+}
+
+// Early extraction (second DRAM pass avoided). k_pack_x is k_pack for a launch that is given a list of sites
+// already known to be variable (`elist`, sorted; found by packing a first chunk of samples): besides everything
+// k_pack does, it stores the bytes of the listed sites, one per (sample, listed site), in X. Every warp parks the
+// PACK_BATCH x 1 KB it has just loaded in its own shared-memory slot (conflict-free STS.128, warp barriers only)
+// and its lanes then pick the warp's listed bytes out of it -- no second read of global memory. k_gather, which
+// pays one 64-byte DRAM atom per (sample, variable site), is then only needed for the sites found variable later
+// (and for the first chunk).
+__global__ void __launch_bounds__(PACK_THREADS, 3)
+k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
+         uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/,
+         uint32_t *__restrict__ ncount, const uint32_t *__restrict__ elist, uint32_t VE, uint8_t *__restrict__ X, uint64_t XP) {
+  // per warp and sample of the batch: 512 B of first halves, 512 B of second halves
+  __shared__ __align__(16) uint8_t wbuf[PACK_THREADS / 32][PACK_BATCH][1024];
+  __shared__ uint8_t slut[256];
+  __shared__ uint32_t s_ncnt[PACK_SCHUNK];
+  for (int i = threadIdx.x; i < PACK_SCHUNK; i += PACK_THREADS) s_ncnt[i] = 0;
+  for (int i = threadIdx.x; i < 256; i += PACK_THREADS) slut[i] = (uint8_t)base_mask(i);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t w = (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x;  // word index
+  const uint64_t s0 = s_begin + (uint64_t)blockIdx.y * PACK_SCHUNK;
+  const uint64_t s1 = min(s_end, s0 + PACK_SCHUNK);
+  const uint64_t site0 = w * 32;
+  const bool in_row = w < npitch;
+  const bool has_sites = site0 < L;
+  uint32_t acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = ~0u;
+  const uint32_t nvalid = has_sites ? (uint32_t)min((uint64_t)32, L - site0) : 0u;
+  const uint32_t validp = pack_validp(nvalid);
+  // listed sites inside this warp's 1024 sites: elist[e_lo .. e_lo + nE)
+  const uint64_t wsite0 = (w - lane) * 32;
+  auto lower = [&](uint64_t key) {
+    uint32_t a = 0, b = VE;
+    while (a < b) {
+      const uint32_t mid = (a + b) >> 1;
+      if (__ldg(elist + mid) < key) a = mid + 1; else b = mid;
+    }
+    return a;
+  };
+  const uint32_t e_lo = lower(wsite0), nE = lower(wsite0 + 1024) - e_lo;
+  // work item i of a batch = (sample t = i / nE, listed site e = i % nE): where its byte sits in the slot and in X
+  auto slot = [&](uint32_t t, uint32_t e) {
+    const uint32_t o = __ldg(elist + e_lo + e) - (uint32_t)wsite0, k = o & 31u;  // lane o/32, byte k
+    return t * 1024 + (o >> 5) * 16 + (k & 15u) + (k >> 4) * 512;
+  };
+  const uint32_t items = nE * PACK_BATCH;
+  // the first two rounds live in registers (a warp rarely lists more than 16 sites); further rounds recompute
+  // (slot address; its bits 10+ are the sample t) and (offset in X relative to the batch's first row)
+  uint32_t it_a[2], it_x[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint32_t i = lane + 32u * r;
+    it_a[r] = 0xFFFFFFFFu;  // t never below `rows`
+    it_x[r] = 0;
+    if (i < items) {
+      const uint32_t t = i / nE, e = i - t * nE;
+      it_a[r] = slot(t, e);
+      it_x[r] = t * (uint32_t)XP + e;  // XP <= L / 16 < 2^27
+    }
+  }
+  uint8_t *mine = &wbuf[warp][0][lane * 16];
+  const uint8_t *wb = &wbuf[warp][0][0];
+  if (in_row) {  // warp-uniform
+    const uint4 kN = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);
+    const uint8_t *src = seqs + s0 * pitch + (has_sites ? site0 : 0);
+    uint32_t *np = nplane + s0 * npitch + w;
+    uint8_t *sp = nsum + s0 * spitch + (w >> 5);
+    uint32_t *cnt = s_ncnt;
+    uint8_t *xrow = X + s0 * XP + e_lo;
+    for (uint64_t b0 = s0; b0 < s1; b0 += PACK_BATCH) {
+      const uint32_t rows = (uint32_t)min((uint64_t)PACK_BATCH, s1 - b0);
+      uint4 va[PACK_BATCH], vb[PACK_BATCH];
+#pragma unroll
+      for (int t = 0; t < PACK_BATCH; ++t) {
+        if (has_sites && (uint32_t)t < rows) {
+          va[t] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch));
+          vb[t] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch) + 1);
+        } else {
+          va[t] = vb[t] = kN;
+        }
+      }
+      if (has_sites && b0 + 2 * PACK_BATCH <= s1) {  // the next batch on its way into L2 while this one is handled
+#pragma unroll
+        for (int t = 0; t < PACK_BATCH; ++t)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(PACK_BATCH + t) * pitch));
+      }
+      if (nE) {  // warp-uniform
+#pragma unroll
+        for (int t = 0; t < PACK_BATCH; ++t) {
+          *reinterpret_cast<uint4 *>(mine + t * 1024) = va[t];
+          *reinterpret_cast<uint4 *>(mine + t * 1024 + 512) = vb[t];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          if ((it_a[r] >> 10) < rows) xrow[it_x[r]] = wb[it_a[r]];
+        for (uint32_t i = lane + 64; i < items; i += 32) {
+          const uint32_t t = i / nE, e = i - t * nE;
+          if (t < rows) xrow[(size_t)t * XP + e] = wb[slot(t, e)];
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int t = 0; t < PACK_BATCH; ++t)
+        if ((uint32_t)t < rows)
+          pack_one_sample(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, slut, acc, validp, lane);
+      src += (size_t)PACK_BATCH * pitch;
+      np += (size_t)PACK_BATCH * npitch;
+      sp += (size_t)PACK_BATCH * spitch;
+      cnt += PACK_BATCH;
+      xrow += (size_t)PACK_BATCH * XP;
+    }
+  }
   __syncthreads();
   for (uint64_t i = threadIdx.x; i < s1 - s0; i += PACK_THREADS)
     if (s_ncnt[i]) atomicAdd(ncount + s0 + i, s_ncnt[i]);
@@ -314,6 +444,90 @@ k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uin
         const uint4 v = make_uint4(A, C, G, T);
         planes[w * Npad + s] = v;    // word-major: tile panels are contiguous 2 KB rows
         planesT[s * Wp + w] = v;     // sample-major: per-pair refinement streams rows
+      }
+    }
+  }
+}
+
+// ---- early-extraction path: byte matrices X[s][e] (byte of listed site e in sample s) -> planes ----------------
+// bytes of the listed sites for a sample range (the scattered DRAM pass, used for the first sample chunk and for
+// the sites found variable only later). One warp per 32 listed sites and sample chunk.
+__global__ void __launch_bounds__(256)
+k_gather_bytes(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint64_t pitch, const uint32_t *__restrict__ list,
+               uint32_t n_list, uint8_t *__restrict__ X, uint64_t XP, uint32_t schunk) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t e = ((uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32 + lane;
+  if (e - lane >= n_list) return;
+  const bool live = e < n_list;
+  const uint64_t site = live ? list[e] : 0;
+  const uint64_t s0 = s_begin + (uint64_t)blockIdx.y * schunk, s1 = min(s_end, s0 + schunk);
+  constexpr int GB = 8;
+  for (uint64_t sb = s0; sb < s1; sb += GB) {
+    uint8_t ch[GB];
+#pragma unroll
+    for (int t = 0; t < GB; ++t) ch[t] = (live && sb + t < s1) ? __ldg(seqs + (sb + t) * pitch + site) : (uint8_t)'N';
+#pragma unroll
+    for (int t = 0; t < GB; ++t)
+      if (live && sb + t < s1) X[(sb + t) * XP + e] = ch[t];
+  }
+}
+
+// where variable site v (sorted list `vlist`) finds its masks: in X (listed early, index in `elist`) or in X2
+// (late, index = v - #early sites before it; elist is a subset of vlist). Also writes the late site list.
+__global__ void k_site_sources(const uint32_t *__restrict__ vlist, uint32_t V, const uint32_t *__restrict__ elist, uint32_t VE,
+                               uint32_t *__restrict__ src, uint32_t *__restrict__ late) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const uint32_t site = vlist[v];
+  uint32_t a = 0, b = VE;
+  while (a < b) {
+    const uint32_t mid = (a + b) >> 1;
+    if (elist[mid] < site) a = mid + 1; else b = mid;
+  }
+  if (a < VE && elist[a] == site) {
+    src[v] = a;
+  } else {
+    src[v] = 0x80000000u | (v - a);
+    late[v - a] = site;
+  }
+}
+
+// bit-slice: one warp per (plane word, sample chunk); lane <-> variable site. Same outputs as k_gather.
+__global__ void __launch_bounds__(256)
+k_slice(const uint8_t *__restrict__ X, uint64_t XP, const uint8_t *__restrict__ X2, uint64_t X2P, const uint32_t *__restrict__ src,
+        uint64_t V, uint64_t n, uint4 *__restrict__ planes, uint64_t Npad, uint4 *__restrict__ planesT, uint64_t Wp, uint32_t schunk,
+        uint32_t *__restrict__ amb_flag) {
+  __shared__ uint8_t lut[256];
+  lut[threadIdx.x] = (uint8_t)base_mask(threadIdx.x);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t w = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w * 32 >= V) return;
+  const uint64_t v = w * 32 + lane;
+  const bool live = v < V;
+  const uint32_t sv = live ? src[v] : 0u;
+  const uint8_t *col = (sv & 0x80000000u) ? X2 + (sv & 0x7FFFFFFFu) : X + sv;
+  const uint64_t cp = (sv & 0x80000000u) ? X2P : XP;
+  const uint64_t s0 = (uint64_t)blockIdx.y * schunk, s1 = min(n, s0 + schunk);
+  constexpr int GB = 8;
+  for (uint64_t sb = s0; sb < s1; sb += GB) {
+    uint8_t mk[GB];
+#pragma unroll
+    for (int t = 0; t < GB; ++t) mk[t] = (live && sb + t < s1) ? __ldg(col + (sb + t) * cp) : (uint8_t)'N';
+#pragma unroll
+    for (int t = 0; t < GB; ++t) {
+      const uint64_t s = sb + t;
+      if (s >= s1) break;
+      const uint32_t m = lut[mk[t]];
+      if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) *amb_flag = 1u;
+      const uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
+      const uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
+      const uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
+      const uint32_t T = __ballot_sync(0xFFFFFFFFu, m & 8);
+      if (lane == 0) {
+        const uint4 o = make_uint4(A, C, G, T);
+        planes[w * Npad + s] = o;
+        planesT[s * Wp + w] = o;
       }
     }
   }
@@ -835,34 +1049,77 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   TRACS_CK(cudaMemsetAsync(nsum.p, 0, nsum.n, st));
   TRACS_CK(cudaMemsetAsync(ncount.p, 0, n * sizeof(uint32_t), st));
 
-  if (L > 0) {
-    dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((n + PACK_SCHUNK - 1) / PACK_SCHUNK));
-    k_pack<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, n, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p);
+  // variable-site list from the column AND: flags -> select; returns the count (synchronises the stream)
+  auto select_sites = [&](DevBuf<uint32_t> &list) -> uint64_t {
+    DevBuf<uint8_t> flags(round_up(L, 8));
+    k_siteflags<<<(unsigned)((Lw * 4 + 255) / 256), 256, 0, st>>>(colmask.p, L, flags.p);
+    list.alloc(L);
+    DevBuf<uint64_t> nsel(1);
+    size_t tmp_bytes = 0;
+    cub::CountingInputIterator<uint32_t> cnt_it(0);
+    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, cnt_it, flags.p, list.p, nsel.p, (int64_t)L, st);
+    DevBuf<uint8_t> tmp(tmp_bytes);
+    cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, cnt_it, flags.p, list.p, nsel.p, (int64_t)L, st);
+    S.kernel_launches += 3;
+    uint64_t cnt = 0;
+    TRACS_CK(cudaMemcpyAsync(&cnt, nsel.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaStreamSynchronize(st));
+    return cnt;
+  };
+  auto launch_pack = [&](uint64_t sa, uint64_t sb, const uint32_t *elist, uint32_t VE, uint8_t *X, uint64_t XP) {
+    if (sb <= sa) return;
+    dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((sb - sa + PACK_SCHUNK - 1) / PACK_SCHUNK));
+    if (VE) {
+      static bool attr = false;
+      if (!attr) {
+        attr = true;
+        TRACS_CK(cudaFuncSetAttribute(k_pack_x, cudaFuncAttributePreferredSharedMemoryCarveout, 60));  // 3 x 34 KB per SM
+        if (getenv("TRACS_INGEST_DBG")) {
+          int occ = 0;
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_x, PACK_THREADS, 0);
+          fprintf(stderr, "[tracs] k_pack_x CTAs per SM: %d\n", occ);
+        }
+      }
+      k_pack_x<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p, elist,
+                                            VE, X, XP);
+    } else {
+      k_pack<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p);
+    }
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
-  } else {
+  };
+  // Early extraction (see k_pack_x): pack a first chunk of samples, list the sites that already vary, and let the
+  // pack of all other samples store those sites' masks on the way. TRACS_INGEST=split / =early overrides the rule.
+  const char *mode_env = getenv("TRACS_INGEST");
+  const uint64_t n_first = PACK_SCHUNK;
+  bool early = L >= (1u << 16) && n >= 8 * n_first && L < (1ull << 31);
+  if (mode_env && !strcmp(mode_env, "split")) early = false;
+  if (mode_env && !strcmp(mode_env, "early")) early = L > 0 && n > n_first && L < (1ull << 31);
+  DevBuf<uint32_t> elist;
+  DevBuf<uint8_t> X;
+  uint64_t VE = 0, XP = 0;
+  if (L == 0) {
     TRACS_CK(cudaMemsetAsync(nplane.p, 0, nplane.n * sizeof(uint32_t), st));
+  } else if (!early) {
+    launch_pack(0, n, nullptr, 0, nullptr, 0);
+  } else {
+    launch_pack(0, n_first, nullptr, 0, nullptr, 0);
+    VE = select_sites(elist);
+    if (VE > L / 16) VE = 0;  // very diverse alignment: the scattered pass reads dense lines anyway
+    if (VE) {
+      XP = round_up(VE, 32);
+      X.alloc(n * XP);
+    } else {
+      early = false;
+    }
+    launch_pack(n_first, n, elist.p, (uint32_t)VE, X.p, XP);
   }
   S.ms_pack += T.stop();
 
   // ---- K0b: variable sites -> planes -----------------------------------------------------
   T.start();
   uint64_t V = 0;
-  if (L > 0) {
-    DevBuf<uint8_t> flags(round_up(L, 8));
-    k_siteflags<<<(unsigned)((Lw * 4 + 255) / 256), 256, 0, st>>>(colmask.p, L, flags.p);
-    S.kernel_launches++;
-    site_idx.alloc(L);
-    DevBuf<uint64_t> nsel(1);
-    size_t tmp_bytes = 0;
-    cub::CountingInputIterator<uint32_t> cnt_it(0);
-    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, cnt_it, flags.p, site_idx.p, nsel.p, (int64_t)L, st);
-    DevBuf<uint8_t> tmp(tmp_bytes);
-    cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, cnt_it, flags.p, site_idx.p, nsel.p, (int64_t)L, st);
-    S.kernel_launches += 2;
-    TRACS_CK(cudaMemcpyAsync(&V, nsel.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaStreamSynchronize(st));
-  }
+  if (L > 0) V = select_sites(site_idx);
   const uint64_t W = (V + 31) / 32;
   const uint32_t Wp = (uint32_t)std::max<uint64_t>(KC, round_up(W, KC));
   g.V = V; g.W = W; g.Wp = Wp; g.Npad = Npad;
@@ -872,13 +1129,35 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   g.planesT.alloc((size_t)Wp * n);
   TRACS_CK(cudaMemsetAsync(g.planes.p, 0xFF, g.planes.n * sizeof(uint4), st));
   TRACS_CK(cudaMemsetAsync(g.planesT.p, 0xFF, g.planesT.n * sizeof(uint4), st));
+  g.partial_ambiguity = false;
   if (W > 0) {
     const uint32_t schunk = 512;
-    dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
     DevBuf<uint32_t> amb(1);
     TRACS_CK(cudaMemsetAsync(amb.p, 0, 4, st));
-    k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, g.planes.p, Npad, g.planesT.p, Wp, schunk, amb.p);
-    S.kernel_launches++;
+    if (!early) {
+      dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
+      k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, g.planes.p, Npad, g.planesT.p, Wp, schunk, amb.p);
+      S.kernel_launches++;
+    } else {
+      // listed sites of the first chunk, late sites of every sample: the scattered pass; then bit-slice
+      const uint64_t VL = V - VE;  // elist is a subset of the final list
+      DevBuf<uint32_t> src(V), late(std::max<uint64_t>(1, VL));
+      DevBuf<uint8_t> X2;
+      const uint64_t X2P = round_up(std::max<uint64_t>(1, VL), 32);
+      k_site_sources<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(site_idx.p, (uint32_t)V, elist.p, (uint32_t)VE, src.p, late.p);
+      k_gather_bytes<<<dim3((unsigned)((VE + 255) / 256), (unsigned)((n_first + schunk - 1) / schunk)), 256, 0, st>>>(
+          dev_seqs, 0, n_first, pitch, elist.p, (uint32_t)VE, X.p, XP, schunk);
+      S.kernel_launches += 2;
+      if (VL) {
+        X2.alloc(n * X2P);
+        k_gather_bytes<<<dim3((unsigned)((VL + 255) / 256), (unsigned)((n + schunk - 1) / schunk)), 256, 0, st>>>(
+            dev_seqs, 0, n, pitch, late.p, (uint32_t)VL, X2.p, X2P, schunk);
+        S.kernel_launches++;
+      }
+      dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
+      k_slice<<<grid, 256, 0, st>>>(X.p, XP, X2.p, X2P, src.p, V, n, g.planes.p, Npad, g.planesT.p, Wp, schunk, amb.p);
+      S.kernel_launches++;
+    }
     TRACS_CK(cudaGetLastError());
     uint32_t h_amb = 0;
     TRACS_CK(cudaMemcpyAsync(&h_amb, amb.p, 4, cudaMemcpyDeviceToHost, st));
