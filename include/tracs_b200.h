@@ -63,7 +63,8 @@ typedef struct tracs_stats {
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t n_candidates;     /* pairs that survived the prefilter sweep (0 if it did not run)       */
   uint64_t swept_wordpairs;  /* 32-site word-pairs the tile kernel actually evaluated               */
-  float ms_pack;             /* ASCII -> column masks + N planes (K0a)                      */
+  uint64_t n_early_sites;    /* sites listed from the first sample chunk and extracted while packing (0: two-pass ingest) */
+  float ms_pack;             /* ASCII -> column masks + N planes (K0a): all pack launches + early site list */
   float ms_compact;          /* variable-site selection + bit-plane gather (K0b)            */
   float ms_sweep;            /* pair tile sweep incl. threshold/compaction epilogue (K1)    */
   float ms_refine;           /* per-pair refinement of prefilter candidates (K1b)           */
@@ -74,6 +75,7 @@ typedef struct tracs_stats {
   float ms_d2h;              /* edge columns device -> host                                  */
   float ms_filter;           /* recombination filter (K4), only when filter != 0             */
   float tc_sweep;            /* 1 if the tile sweep launches ran on the tensor cores (k_sweep_tc) */
+  float ms_pack_main;        /* the main pack launch alone: k_pack_x over samples 256.. (early extraction) or k_pack over all */
 } tracs_stats_t;
 
 /* Options shared by the matrix-input entry points. Zero-initialise, then set. */

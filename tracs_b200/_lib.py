@@ -24,8 +24,8 @@ class Edges(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("n_samples", "seq_length", "n_variable_sites", "n_words", "n_tiles", "n_pairs",
                                           "n_edges", "kernel_launches", "h2d_bytes", "d2h_bytes", "n_candidates",
-                                          "swept_wordpairs")] + \
-               [(k, C.c_float) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_total", "ms_d2h", "ms_filter", "tc_sweep")]
+                                          "swept_wordpairs", "n_early_sites")] + \
+               [(k, C.c_float) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_total", "ms_d2h", "ms_filter", "tc_sweep", "ms_pack_main")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -270,7 +270,7 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint6
 
 // Early extraction (second DRAM pass avoided). k_pack_x is k_pack for a launch that is given a list of sites
 // already known to be variable (`elist`, sorted; found by packing a first chunk of samples): besides everything
-// k_pack does, it stores the bytes of the listed sites, one per (sample, listed site), in X. Every warp parks the
+// k_pack does, it stores the masks of the listed sites, one byte per (sample, listed site), in X. Every warp parks the
 // PACK_BATCH x 1 KB it has just loaded in its own shared-memory slot (conflict-free STS.128, warp barriers only)
 // and its lanes then pick the warp's listed bytes out of it -- no second read of global memory. k_gather, which
 // pays one 64-byte DRAM atom per (sample, variable site), is then only needed for the sites found variable later
@@ -364,10 +364,10 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 2; ++r)
-          if ((it_a[r] >> 10) < rows) xrow[it_x[r]] = wb[it_a[r]];
+          if ((it_a[r] >> 10) < rows) xrow[it_x[r]] = slut[wb[it_a[r]]];
         for (uint32_t i = lane + 64; i < items; i += 32) {
           const uint32_t t = i / nE, e = i - t * nE;
-          if (t < rows) xrow[(size_t)t * XP + e] = wb[slot(t, e)];
+          if (t < rows) xrow[(size_t)t * XP + e] = slut[wb[slot(t, e)]];
         }
         __syncwarp();
       }
@@ -449,12 +449,15 @@ k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uin
   }
 }
 
-// ---- early-extraction path: byte matrices X[s][e] (byte of listed site e in sample s) -> planes ----------------
-// bytes of the listed sites for a sample range (the scattered DRAM pass, used for the first sample chunk and for
+// ---- early-extraction path: byte matrices X[s][e] (mask of listed site e in sample s) -> planes ----------------
+// masks of the listed sites for a sample range (the scattered DRAM pass, used for the first sample chunk and for
 // the sites found variable only later). One warp per 32 listed sites and sample chunk.
 __global__ void __launch_bounds__(256)
 k_gather_bytes(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint64_t pitch, const uint32_t *__restrict__ list,
                uint32_t n_list, uint8_t *__restrict__ X, uint64_t XP, uint32_t schunk) {
+  __shared__ uint8_t lut[256];
+  lut[threadIdx.x] = (uint8_t)base_mask(threadIdx.x);
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t e = ((uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32 + lane;
   if (e - lane >= n_list) return;
@@ -468,7 +471,7 @@ k_gather_bytes(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_en
     for (int t = 0; t < GB; ++t) ch[t] = (live && sb + t < s1) ? __ldg(seqs + (sb + t) * pitch + site) : (uint8_t)'N';
 #pragma unroll
     for (int t = 0; t < GB; ++t)
-      if (live && sb + t < s1) X[(sb + t) * XP + e] = ch[t];
+      if (live && sb + t < s1) X[(sb + t) * XP + e] = lut[ch[t]];
   }
 }
 
@@ -492,42 +495,87 @@ __global__ void k_site_sources(const uint32_t *__restrict__ vlist, uint32_t V, c
   }
 }
 
-// bit-slice: one warp per (plane word, sample chunk); lane <-> variable site. Same outputs as k_gather.
+// bit-slice the mask bytes into planes; same outputs as k_gather. One warp per PAIR of plane words and sample chunk.
+// Fast path (the 64 sites of the pair sit in 64 consecutive, 16-byte aligned columns of X): lane <-> sample, each lane
+// loads its 64 mask bytes and gathers bit b of every byte with a multiply (SWAR), so that a warp finishes 32 samples x
+// 2 words per pass with coalesced stores to both layouts. Otherwise (late sites mixed in, tail): lane <-> site, ballots.
+__device__ __forceinline__ uint32_t slice_bits4(uint32_t r, int b) {  // bit j of the result = bit b of byte j of r
+  return (((r >> b) & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint4 slice_word(const uint4 &q0, const uint4 &q1) {  // 32 mask bytes -> A, C, G, T words
+  const uint32_t r[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v |= (slice_bits4(r[k], b) & 0xFu) << (4 * k);
+    o[b] = v;
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ bool slice_ambiguous(const uint4 &p) {  // some site with 2 or 3 of the 4 bits
+  const uint32_t two = (p.x & p.y) | (p.x & p.z) | (p.x & p.w) | (p.y & p.z) | (p.y & p.w) | (p.z & p.w);
+  return (two & ~(p.x & p.y & p.z & p.w)) != 0u;
+}
+
 __global__ void __launch_bounds__(256)
 k_slice(const uint8_t *__restrict__ X, uint64_t XP, const uint8_t *__restrict__ X2, uint64_t X2P, const uint32_t *__restrict__ src,
         uint64_t V, uint64_t n, uint4 *__restrict__ planes, uint64_t Npad, uint4 *__restrict__ planesT, uint64_t Wp, uint32_t schunk,
         uint32_t *__restrict__ amb_flag) {
-  __shared__ uint8_t lut[256];
-  lut[threadIdx.x] = (uint8_t)base_mask(threadIdx.x);
-  __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
-  const uint64_t w = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (w * 32 >= V) return;
-  const uint64_t v = w * 32 + lane;
-  const bool live = v < V;
-  const uint32_t sv = live ? src[v] : 0u;
-  const uint8_t *col = (sv & 0x80000000u) ? X2 + (sv & 0x7FFFFFFFu) : X + sv;
-  const uint64_t cp = (sv & 0x80000000u) ? X2P : XP;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 2;  // first word of the pair
+  if (w0 * 32 >= V) return;
   const uint64_t s0 = (uint64_t)blockIdx.y * schunk, s1 = min(n, s0 + schunk);
-  constexpr int GB = 8;
-  for (uint64_t sb = s0; sb < s1; sb += GB) {
-    uint8_t mk[GB];
+  // fast path test: both words complete, sources = 64 consecutive columns of X starting at a multiple of 16
+  bool fast = (w0 + 2) * 32 <= V;
+  uint32_t base = 0;
+  if (fast) {
+    const uint32_t a = src[w0 * 32 + lane], b = src[w0 * 32 + 32 + lane];
+    base = __shfl_sync(0xFFFFFFFFu, a, 0);
+    fast = __all_sync(0xFFFFFFFFu, a == base + lane && b == base + 32 + lane) && !(base & 0x80000000u) && (base & 15u) == 0;
+  }
+  if (fast) {
+    bool amb = false;
+    for (uint64_t s = s0 + lane; s < s1; s += 32) {
+      const uint4 *row = reinterpret_cast<const uint4 *>(X + s * XP + base);
+      const uint4 q0 = __ldg(row), q1 = __ldg(row + 1), q2 = __ldg(row + 2), q3 = __ldg(row + 3);
+      const uint4 pa = slice_word(q0, q1), pb = slice_word(q2, q3);
+      amb |= slice_ambiguous(pa) | slice_ambiguous(pb);
+      planes[w0 * Npad + s] = pa;
+      planes[(w0 + 1) * Npad + s] = pb;
+      planesT[s * Wp + w0] = pa;
+      planesT[s * Wp + w0 + 1] = pb;
+    }
+    if (__any_sync(0xFFFFFFFFu, amb) && lane == 0) *amb_flag = 1u;
+    return;
+  }
+  for (uint64_t w = w0; w < w0 + 2 && w * 32 < V; ++w) {
+    const uint64_t v = w * 32 + lane;
+    const bool live = v < V;
+    const uint32_t sv = live ? src[v] : 0u;
+    const uint8_t *col = (sv & 0x80000000u) ? X2 + (sv & 0x7FFFFFFFu) : X + sv;
+    const uint64_t cp = (sv & 0x80000000u) ? X2P : XP;
+    constexpr int GB = 8;
+    for (uint64_t sb = s0; sb < s1; sb += GB) {
+      uint8_t mk[GB];
 #pragma unroll
-    for (int t = 0; t < GB; ++t) mk[t] = (live && sb + t < s1) ? __ldg(col + (sb + t) * cp) : (uint8_t)'N';
+      for (int t = 0; t < GB; ++t) mk[t] = (live && sb + t < s1) ? __ldg(col + (sb + t) * cp) : (uint8_t)15;
 #pragma unroll
-    for (int t = 0; t < GB; ++t) {
-      const uint64_t s = sb + t;
-      if (s >= s1) break;
-      const uint32_t m = lut[mk[t]];
-      if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) *amb_flag = 1u;
-      const uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
-      const uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
-      const uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
-      const uint32_t T = __ballot_sync(0xFFFFFFFFu, m & 8);
-      if (lane == 0) {
-        const uint4 o = make_uint4(A, C, G, T);
-        planes[w * Npad + s] = o;
-        planesT[s * Wp + w] = o;
+      for (int t = 0; t < GB; ++t) {
+        const uint64_t s = sb + t;
+        if (s >= s1) break;
+        const uint32_t m = mk[t];
+        if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) *amb_flag = 1u;
+        const uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
+        const uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
+        const uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
+        const uint32_t T = __ballot_sync(0xFFFFFFFFu, m & 8);
+        if (lane == 0) {
+          const uint4 o = make_uint4(A, C, G, T);
+          planes[w * Npad + s] = o;
+          planesT[s * Wp + w] = o;
+        }
       }
     }
   }
@@ -1101,7 +1149,10 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   if (L == 0) {
     TRACS_CK(cudaMemsetAsync(nplane.p, 0, nplane.n * sizeof(uint32_t), st));
   } else if (!early) {
+    Timer Tm(st);
+    Tm.start();
     launch_pack(0, n, nullptr, 0, nullptr, 0);
+    S.ms_pack_main += Tm.stop();
   } else {
     launch_pack(0, n_first, nullptr, 0, nullptr, 0);
     VE = select_sites(elist);
@@ -1112,7 +1163,11 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
     } else {
       early = false;
     }
+    Timer Tm(st);
+    Tm.start();
     launch_pack(n_first, n, elist.p, (uint32_t)VE, X.p, XP);
+    S.ms_pack_main += Tm.stop();
+    S.n_early_sites += VE;
   }
   S.ms_pack += T.stop();
 
@@ -1154,7 +1209,7 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
             dev_seqs, 0, n, pitch, late.p, (uint32_t)VL, X2.p, X2P, schunk);
         S.kernel_launches++;
       }
-      dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
+      dim3 grid((unsigned)((W + 15) / 16), (unsigned)((n + schunk - 1) / schunk));
       k_slice<<<grid, 256, 0, st>>>(X.p, XP, X2.p, X2P, src.p, V, n, g.planes.p, Npad, g.planesT.p, Wp, schunk, amb.p);
       S.kernel_launches++;
     }
