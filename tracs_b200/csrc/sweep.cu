@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <memory>
 #include <stdexcept>
+#include <type_traits>
 
 #include "common.cuh"
 #include "trans.cuh"
@@ -173,21 +174,18 @@ __device__ __forceinline__ void pack_one_sample(const uint4 &a, const uint4 &b, 
 __device__ __forceinline__ void pack_rows(const uint8_t *src, uint64_t pitch, uint32_t rows, bool has_sites, uint32_t *np,
                                           uint64_t npitch, uint8_t *sp, uint64_t spitch, uint32_t *cnt, const uint8_t *slut,
                                           uint32_t (&acc)[8], uint32_t validp, uint32_t lane) {
-  const uint4 kN = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);  // 'N': neutral for the column AND
   auto load = [](const uint4 *p) { return __ldcs(p); };
   uint32_t r = 0;
   for (; r + PACK_BATCH <= rows; r += PACK_BATCH) {
     uint4 va[PACK_BATCH], vb[PACK_BATCH];
 #pragma unroll
     for (int t = 0; t < PACK_BATCH; ++t) {
-      if (has_sites) {
-        va[t] = load(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch));
-        vb[t] = load(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch) + 1);
-      } else {
-        va[t] = vb[t] = kN;
-      }
+      // lanes past the end of the alignment read the start of the row instead: whatever they see is masked out
+      // (validp == 0, no column word), so the loads need no per-lane predicate
+      va[t] = load(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch));
+      vb[t] = load(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch) + 1);
     }
-    if (has_sites && r + 2 * PACK_BATCH <= rows) {  // the next batch on its way into L2 while this one is handled
+    if (r + 2 * PACK_BATCH <= rows) {  // the next batch on its way into L2 while this one is handled
 #pragma unroll
       for (int t = 0; t < PACK_BATCH; ++t) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(PACK_BATCH + t) * pitch));
     }
@@ -200,11 +198,7 @@ __device__ __forceinline__ void pack_rows(const uint8_t *src, uint64_t pitch, ui
     cnt += PACK_BATCH;
   }
   for (; r < rows; ++r) {  // tail
-    uint4 va = kN, vb = kN;
-    if (has_sites) {
-      va = load(reinterpret_cast<const uint4 *>(src));
-      vb = load(reinterpret_cast<const uint4 *>(src) + 1);
-    }
+    const uint4 va = load(reinterpret_cast<const uint4 *>(src)), vb = load(reinterpret_cast<const uint4 *>(src) + 1);
     pack_one_sample(va, vb, np, sp, cnt, slut, acc, validp, lane);
     src += pitch; np += npitch; sp += spitch; ++cnt;
   }
@@ -338,19 +332,23 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
     uint8_t *sp = nsum + s0 * spitch + (w >> 5);
     uint32_t *cnt = s_ncnt;
     uint8_t *xrow = X + s0 * XP + e_lo;
-    for (uint64_t b0 = s0; b0 < s1; b0 += PACK_BATCH) {
-      const uint32_t rows = (uint32_t)min((uint64_t)PACK_BATCH, s1 - b0);
+    const bool more_items = items > 64;  // warp-uniform
+    // one batch of `rows` samples (FULL: rows == PACK_BATCH, nothing predicated on it)
+    auto batch = [&](auto full_tag, uint32_t rows, bool prefetch_next) {
+      constexpr bool FULL = decltype(full_tag)::value;
       uint4 va[PACK_BATCH], vb[PACK_BATCH];
 #pragma unroll
       for (int t = 0; t < PACK_BATCH; ++t) {
-        if (has_sites && (uint32_t)t < rows) {
+        // lanes past the end of the alignment read the start of the row instead: whatever they see is masked out
+        // (validp == 0, no column word, never listed), so the loads need no per-lane predicate
+        if (FULL || (uint32_t)t < rows) {
           va[t] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch));
           vb[t] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)t * pitch) + 1);
         } else {
           va[t] = vb[t] = kN;
         }
       }
-      if (has_sites && b0 + 2 * PACK_BATCH <= s1) {  // the next batch on its way into L2 while this one is handled
+      if (prefetch_next) {  // the next batch on its way into L2 while this one is handled
 #pragma unroll
         for (int t = 0; t < PACK_BATCH; ++t)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(PACK_BATCH + t) * pitch));
@@ -363,24 +361,31 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
         }
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-          if ((it_a[r] >> 10) < rows) xrow[it_x[r]] = slut[wb[it_a[r]]];
-        for (uint32_t i = lane + 64; i < items; i += 32) {
-          const uint32_t t = i / nE, e = i - t * nE;
-          if (t < rows) xrow[(size_t)t * XP + e] = slut[wb[slot(t, e)]];
+        for (int r = 0; r < 2; ++r) {  // the lookups run unconditionally (slot 0 for idle lanes), only the store is predicated
+          const uint8_t m = slut[wb[it_a[r] & 0xFFFu]];
+          if (FULL ? it_a[r] != 0xFFFFFFFFu : (it_a[r] >> 10) < rows) xrow[it_x[r]] = m;
         }
+        if (more_items)
+          for (uint32_t i = lane + 64; i < items; i += 32) {
+            const uint32_t t = i / nE, e = i - t * nE;
+            if (t < rows) xrow[(size_t)t * XP + e] = slut[wb[slot(t, e)]];
+          }
         __syncwarp();
       }
 #pragma unroll
       for (int t = 0; t < PACK_BATCH; ++t)
-        if ((uint32_t)t < rows)
+        if (FULL || (uint32_t)t < rows)
           pack_one_sample(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, slut, acc, validp, lane);
       src += (size_t)PACK_BATCH * pitch;
       np += (size_t)PACK_BATCH * npitch;
       sp += (size_t)PACK_BATCH * spitch;
       cnt += PACK_BATCH;
       xrow += (size_t)PACK_BATCH * XP;
-    }
+    };
+    uint64_t b0 = s0;
+    for (; b0 + 2 * PACK_BATCH <= s1; b0 += PACK_BATCH) batch(std::true_type{}, PACK_BATCH, true);
+    for (; b0 + PACK_BATCH <= s1; b0 += PACK_BATCH) batch(std::true_type{}, PACK_BATCH, false);
+    if (b0 < s1) batch(std::false_type{}, (uint32_t)(s1 - b0), false);
   }
   __syncthreads();
   for (uint64_t i = threadIdx.x; i < s1 - s0; i += PACK_THREADS)
