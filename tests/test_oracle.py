@@ -113,7 +113,10 @@ def test_live_reference(oracle_mod, ref_mod, tmp_path):
         p = str(tmp_path / ("t%d.fa%s" % (trial, ".gz" if trial % 2 else "")))
         synth.write_fasta(p, s, width=[0, 60, 7][trial % 3], descriptions=bool(trial % 2))
         for dist, filt in ((3, False), (IMAX, False), (IMAX, True)):
-            a = ref_mod.pairsnp(fasta=[p], n_threads=1 + trial % 3, dist=dist, filter=filt)
+            # filter=True is only safe single-threaded in the reference: cached_binomial_cdf (src/pairsnp.hpp:40-58) keeps a
+            # function-static std::map that the OpenMP pair loop (:380-432) inserts into without a lock -- with more
+            # threads the run corrupts the heap now and then (seen here as a crash at interpreter exit)
+            a = ref_mod.pairsnp(fasta=[p], n_threads=1 if filt else 1 + trial % 3, dist=dist, filter=filt)
             b = oracle_mod.pairsnp([p], n_threads=2, dist=dist, filter=filt)
             assert all(list(a[t]) == b[t] for t in range(6))
     N = np.repeat(np.arange(0, 30), 10)
