@@ -1127,11 +1127,6 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
       if (!attr) {
         attr = true;
         TRACS_CK(cudaFuncSetAttribute(k_pack_x, cudaFuncAttributePreferredSharedMemoryCarveout, 60));  // 3 x 34 KB per SM
-        if (getenv("TRACS_INGEST_DBG")) {
-          int occ = 0;
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_x, PACK_THREADS, 0);
-          fprintf(stderr, "[tracs] k_pack_x CTAs per SM: %d\n", occ);
-        }
       }
       k_pack_x<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p, elist,
                                             VE, X, XP);
