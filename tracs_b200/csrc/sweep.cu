@@ -1493,6 +1493,55 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       S.kernel_launches += 3;
       S.ms_filter += T.stop();
     }
+    // Edge columns leave for the host on a side stream as soon as they exist, under the compared-sites kernel:
+    // (rows, cols, dist[, filt]) right away, the likelihood columns after the transmission kernels (which therefore run
+    // BEFORE k_ncomp), the compared-sites column last on the main stream.
+    static thread_local cudaStream_t cs = nullptr;
+    static thread_local cudaEvent_t ev_cols = nullptr, ev_trans = nullptr;
+    static thread_local int cs_dev = -1;
+    int cur_dev = 0;
+    TRACS_CK(cudaGetDevice(&cur_dev));
+    if (!cs || cs_dev != cur_dev) {  // (a stream made for another device is left to the driver)
+      cs_dev = cur_dev;
+      TRACS_CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      TRACS_CK(cudaEventCreateWithFlags(&ev_cols, cudaEventDisableTiming));
+      TRACS_CK(cudaEventCreateWithFlags(&ev_trans, cudaEventDisableTiming));
+    }
+    const size_t old = out.rows.size();
+    out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E);
+    if (want_n) out.ncomp.resize(old + E);
+    if (o.filter) out.filt.resize(old + E);
+    if (fuse_trans) { out.p0_log.resize(old + E); out.eK.resize(old + E); out.datediff.resize(old + E); }
+    TRACS_CK(cudaEventRecord(ev_cols, st));
+    TRACS_CK(cudaStreamWaitEvent(cs, ev_cols, 0));
+    if (o.filter) TRACS_CK(cudaMemcpyAsync(out.filt.data() + old, d_filt64.p, E * 8, cudaMemcpyDeviceToHost, cs));
+    TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, d_rows.p, E * 8, cudaMemcpyDeviceToHost, cs));
+    TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, d_cols.p, E * 8, cudaMemcpyDeviceToHost, cs));
+    TRACS_CK(cudaMemcpyAsync(out.dist.data() + old, d_dist.p, E * 8, cudaMemcpyDeviceToHost, cs));
+    DevBuf<double> d_p0, d_eK, d_dt;
+    if (fuse_trans) {
+      T.start();
+      d_p0.alloc(E); d_eK.alloc(E); d_dt.alloc(E);
+      TRACS_CK(cudaMemsetAsync(used.p, 0, lut_size, st));
+      // with the filter on, the likelihood is fed the filtered distance (tracs/distance.py:182-192)
+      const uint32_t *dtrans = o.filter ? d_filt32.p : dv2.p;
+      k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dtrans, E, d_days.p, DD, used.p);
+      cub::CountingInputIterator<uint32_t> cnt_it(0);
+      cub::DeviceSelect::Flagged(sel_tmp.p, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
+      k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, st>>>(key_idx.p, n_keys.p, DD, d_lg.p, o.lamb, o.beta, o.threshold_Ek,
+                                                                    p0_lut.p, eK_lut.p);
+      k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dtrans, E, d_days.p, DD, p0_lut.p, eK_lut.p, d_p0.p,
+                                                                 d_eK.p, d_dt.p);
+      S.kernel_launches += 5;
+      TRACS_CK(cudaGetLastError());
+      S.ms_trans += T.stop();
+      TRACS_CK(cudaEventRecord(ev_trans, st));
+      TRACS_CK(cudaStreamWaitEvent(cs, ev_trans, 0));
+      TRACS_CK(cudaMemcpyAsync(out.p0_log.data() + old, d_p0.p, E * 8, cudaMemcpyDeviceToHost, cs));
+      TRACS_CK(cudaMemcpyAsync(out.eK.data() + old, d_eK.p, E * 8, cudaMemcpyDeviceToHost, cs));
+      TRACS_CK(cudaMemcpyAsync(out.datediff.data() + old, d_dt.p, E * 8, cudaMemcpyDeviceToHost, cs));
+      S.d2h_bytes += E * 24;
+    }
     if (want_n) {
       T.start();
       d_nc.alloc(E);
@@ -1517,24 +1566,6 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       TRACS_CK(cudaGetLastError());
       S.ms_ncomp += T.stop();
     }
-    DevBuf<double> d_p0, d_eK, d_dt;
-    if (fuse_trans) {
-      T.start();
-      d_p0.alloc(E); d_eK.alloc(E); d_dt.alloc(E);
-      TRACS_CK(cudaMemsetAsync(used.p, 0, lut_size, st));
-      // with the filter on, the likelihood is fed the filtered distance (tracs/distance.py:182-192)
-      const uint32_t *dtrans = o.filter ? d_filt32.p : dv2.p;
-      k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dtrans, E, d_days.p, DD, used.p);
-      cub::CountingInputIterator<uint32_t> cnt_it(0);
-      cub::DeviceSelect::Flagged(sel_tmp.p, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
-      k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, st>>>(key_idx.p, n_keys.p, DD, d_lg.p, o.lamb, o.beta, o.threshold_Ek,
-                                                                    p0_lut.p, eK_lut.p);
-      k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dtrans, E, d_days.p, DD, p0_lut.p, eK_lut.p, d_p0.p,
-                                                                 d_eK.p, d_dt.p);
-      S.kernel_launches += 5;
-      TRACS_CK(cudaGetLastError());
-      S.ms_trans += T.stop();
-    }
     if (o.keep_on_device && bands.size() == 1) {
       void *dp = nullptr;
       TRACS_CK(cudaMalloc(&dp, std::max<size_t>(32, 32 * E)));
@@ -1545,26 +1576,10 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
                                                                (uint8_t *)dp);
       S.kernel_launches++;
     }
-    const size_t old = out.rows.size();
     T.start();
-    if (fuse_trans) {
-      out.p0_log.resize(old + E); out.eK.resize(old + E); out.datediff.resize(old + E);
-      TRACS_CK(cudaMemcpyAsync(out.p0_log.data() + old, d_p0.p, E * 8, cudaMemcpyDeviceToHost, st));
-      TRACS_CK(cudaMemcpyAsync(out.eK.data() + old, d_eK.p, E * 8, cudaMemcpyDeviceToHost, st));
-      TRACS_CK(cudaMemcpyAsync(out.datediff.data() + old, d_dt.p, E * 8, cudaMemcpyDeviceToHost, st));
-      S.d2h_bytes += E * 24;
-    }
-    out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E);
-    if (want_n) out.ncomp.resize(old + E);
-    if (o.filter) {
-      out.filt.resize(old + E);
-      TRACS_CK(cudaMemcpyAsync(out.filt.data() + old, d_filt64.p, E * 8, cudaMemcpyDeviceToHost, st));
-    }
-    TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaMemcpyAsync(out.dist.data() + old, d_dist.p, E * 8, cudaMemcpyDeviceToHost, st));
     if (want_n) TRACS_CK(cudaMemcpyAsync(out.ncomp.data() + old, d_nc.p, E * 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaStreamSynchronize(st));
+    TRACS_CK(cudaStreamSynchronize(cs));
     S.ms_d2h += T.stop();
     S.d2h_bytes += E * 8 * (want_n ? 4 : 3);
     S.n_edges += E;
