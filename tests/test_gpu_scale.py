@@ -39,12 +39,21 @@ def _pair_truth(a, b):
 
 
 @pytest.mark.parametrize("n,L,clusters,dist", [(12000, 400_000, 150, 20), (3000, 2_000_000, 40, 20)])
-def test_large_properties(n, L, clusters, dist):
+def test_large_properties(n, L, clusters, dist, monkeypatch):
     aln = DevAln(n, L, seed=11, p_var=0.03, n_clusters=clusters, mu=5.0, p_N=1e-3, p_amb=0.002, gc=0.5)
     try:
         res = tracs_b200.pairsnp_device(aln.p.value, n, L, aln.pitch, dist=dist)
         st = tracs_b200.last_stats()
         assert st["ms_refine"] > 0, "filter-and-refine path expected at this shape"
+        assert st["n_early_sites"] > 0, "early-extraction ingest expected at this shape"
+        # the two-pass ingest (k_pack + k_gather) gives the same edge table and the same variable sites
+        monkeypatch.setenv("TRACS_INGEST", "split")
+        two = tracs_b200.pairsnp_device(aln.p.value, n, L, aln.pitch, dist=dist)
+        st2 = tracs_b200.last_stats()
+        monkeypatch.delenv("TRACS_INGEST")
+        assert st2["n_early_sites"] == 0 and st2["n_variable_sites"] == st["n_variable_sites"]
+        for k in ("rows", "cols", "dist", "ncomp"):
+            assert np.array_equal(res[k], two[k])
         E = len(res["rows"])
         assert E > 1000
         key = (res["rows"] << np.uint64(32)) | res["cols"]
