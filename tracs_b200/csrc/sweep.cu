@@ -353,12 +353,18 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
         for (int t = 0; t < PACK_BATCH; ++t)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(PACK_BATCH + t) * pitch));
       }
-      if (nE) {  // warp-uniform
+      // every sample is parked in the warp's slot right before it is packed (the later loads of the batch are still in
+      // flight then); the listed bytes are picked out once the whole batch is in place
 #pragma unroll
-        for (int t = 0; t < PACK_BATCH; ++t) {
+      for (int t = 0; t < PACK_BATCH; ++t) {
+        if (nE) {  // warp-uniform
           *reinterpret_cast<uint4 *>(mine + t * 1024) = va[t];
           *reinterpret_cast<uint4 *>(mine + t * 1024 + 512) = vb[t];
         }
+        if (FULL || (uint32_t)t < rows)
+          pack_one_sample(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, slut, acc, validp, lane);
+      }
+      if (nE) {  // warp-uniform
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 2; ++r) {  // the lookups run unconditionally (slot 0 for idle lanes), only the store is predicated
@@ -372,10 +378,6 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
           }
         __syncwarp();
       }
-#pragma unroll
-      for (int t = 0; t < PACK_BATCH; ++t)
-        if (FULL || (uint32_t)t < rows)
-          pack_one_sample(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, slut, acc, validp, lane);
       src += (size_t)PACK_BATCH * pitch;
       np += (size_t)PACK_BATCH * npitch;
       sp += (size_t)PACK_BATCH * spitch;
