@@ -269,6 +269,8 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint6
 // and its lanes then pick the warp's listed bytes out of it -- no second read of global memory. k_gather, which
 // pays one 64-byte DRAM atom per (sample, variable site), is then only needed for the sites found variable later
 // (and for the first chunk).
+constexpr int PACKX_AHEAD = 1;  // batches between the L2 prefetch and the loads
+
 __global__ void __launch_bounds__(PACK_THREADS, 3)
 k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
          uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/,
@@ -351,7 +353,7 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
       if (prefetch_next) {  // the next batch on its way into L2 while this one is handled
 #pragma unroll
         for (int t = 0; t < PACK_BATCH; ++t)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(PACK_BATCH + t) * pitch));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(PACKX_AHEAD * PACK_BATCH + t) * pitch));
       }
       // every sample is parked in the warp's slot right before it is packed (the later loads of the batch are still in
       // flight then); the listed bytes are picked out once the whole batch is in place
@@ -385,7 +387,7 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
       xrow += (size_t)PACK_BATCH * XP;
     };
     uint64_t b0 = s0;
-    for (; b0 + 2 * PACK_BATCH <= s1; b0 += PACK_BATCH) batch(std::true_type{}, PACK_BATCH, true);
+    for (; b0 + (PACKX_AHEAD + 1) * PACK_BATCH <= s1; b0 += PACK_BATCH) batch(std::true_type{}, PACK_BATCH, true);
     for (; b0 + PACK_BATCH <= s1; b0 += PACK_BATCH) batch(std::true_type{}, PACK_BATCH, false);
     if (b0 < s1) batch(std::false_type{}, (uint32_t)(s1 - b0), false);
   }
