@@ -498,9 +498,10 @@ def main():
                      "ms_per_launch": ms_main, "algorithmic_bytes": pack_bytes, "samples_in_launch": n_main, "early_sites": n_early,
                      "peak_source": hbm_src}
         prefiltered = avg("n_candidates") > 0 or avg("ms_refine") > 0
+        pf_words = int(round(avg("swept_wordpairs") / max(1.0, avg("n_pairs"))))  # window of the prefilter launch(es), in 32-site words
         on_tc = avg("tc_sweep") > 0.5
         roof_sweep = (tc_roof if on_tc else sweep_roof)(avg("swept_wordpairs"), avg("ms_sweep"),
-                                                        "prefilter launch (first 64 words of every pair)" if prefiltered else "full-length sweep")
+                                                        "prefilter launch (first %d words of every pair)" % pf_words if prefiltered else "full-length sweep")
         # the same tile kernel forced over the full length (what an unthresholded / dense run executes)
         t_full = []
         for _ in range(3):
@@ -547,7 +548,7 @@ def main():
                        "msas": n_msa,
                        "parallelism": ("triangle row-blocks of one MSA dealt boustrophedon over %d GPUs; ingest replicated" % world) if by_tiles
                        else ("%d independent MSA(s), one per GPU (tracs/distance.py:159 loop); edge lists gathered to rank 0" % world),
-                       "algorithm": "exact filter-and-refine: tile sweep over the first 64 words of every pair, per-pair refinement of the "
+                       "algorithm": "exact filter-and-refine: tile sweep over the first %d words of every pair, per-pair refinement of the " % pf_words +
                                     "survivors; roofline_kernels.k_sweep_full_length gives the same step with the full-length tile sweep",
                        "l2": "inputs (%.1f GB ASCII) larger than L2; no flush needed" % (n * pitch / 1e9)},
             "clocks": clk, "gpu_launches": launches, "roofline": roof,

@@ -78,7 +78,8 @@ def test_early_extraction_ingest_matches_oracle(oracle_mod, monkeypatch, n, L, p
     assert tracs_b200.last_stats()["n_variable_sites"] == st_early["n_variable_sites"]
 
 
-@pytest.mark.parametrize("n_clusters,dist,expect", [(60, 20, "refine"), (3, 20, "fallback"), (60, 0, "refine"), (3, 2047, "any")])
+@pytest.mark.parametrize("n_clusters,dist,expect", [(60, 20, "refine"), (3, 20, "fallback"), (60, 0, "refine"), (3, 2047, "any"),
+                                                    (60, 100, "any"), (60, 300, "any")])
 def test_prefilter_refine_and_fallback(oracle_mod, n_clusters, dist, expect):
     # long enough (>= 256 words of variable sites) for the filter-and-refine path to engage
     s = synth.generate(300, 200_000, p_var=0.06, n_clusters=n_clusters, mu=4, p_N=0.002, p_amb=0.01, seed=41 + n_clusters)
@@ -87,9 +88,11 @@ def test_prefilter_refine_and_fallback(oracle_mod, n_clusters, dist, expect):
     _cmp(res, oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4))
     assert st["n_words"] >= 256
     if expect == "refine":
-        assert st["ms_refine"] > 0 and st["swept_wordpairs"] == st["n_pairs"] * 64
+        # dist 0 / 20: the 16-word window (512 variable sites) is enough
+        assert st["ms_refine"] > 0 and st["swept_wordpairs"] == st["n_pairs"] * 16
     elif expect == "fallback":
-        assert st["ms_refine"] == 0 and st["n_candidates"] > 0 and st["swept_wordpairs"] > st["n_pairs"] * 64
+        # too many pairs survive the 16-word and then the 64-word window: both attempts, then the full-length sweep
+        assert st["ms_refine"] == 0 and st["n_candidates"] > 0 and st["swept_wordpairs"] > st["n_pairs"] * (16 + 64)
     full = tracs_b200.pairsnp_matrix(s, dist=dist, full_sweep=True)
     st2 = tracs_b200.last_stats()
     assert st2["n_candidates"] == 0 and st2["ms_refine"] == 0

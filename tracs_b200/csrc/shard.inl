@@ -101,7 +101,7 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
     DevBuf<unsigned long long> counter(1);
     TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
     const bool tc_ok = o.sweep_variant != 1 && !g.partial_ambiguity;
-    const uint32_t words = std::min<uint32_t>(PREFILTER_WORDS, g.Wp);  // Wp is a multiple of KC
+    const uint32_t words = std::min<uint32_t>(prefilter_words(o.dist), g.Wp);  // Wp is a multiple of KC; any prefix gives a lower bound
     DevBuf<uint32_t> d_rb(std::max<size_t>(1, plan.my_rb.size())), d_prefix(plan.my_rb.size() + 1);
     size_t k0 = 0;
     T.start();

@@ -643,7 +643,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 constexpr int SWEEP_THREADS = 256;
 constexpr int STAGE_U4 = KC * TILE;  // uint4 per stage per side
-constexpr uint32_t PREFILTER_WORDS = 64;  // 2048 variable sites
+constexpr uint32_t PREFILTER_WORDS = 64;  // widest prefilter window: 2048 variable sites
+// Prefilter window for a threshold: 32 * words sites must be many times the allowed distance for unrelated pairs to
+// fall out of it; 8 sites per allowed SNP, in steps of 16 words (dist <= 63: 16 words = 512 sites).
+static inline uint32_t prefilter_words(int64_t dist) {
+  const uint64_t w = ((uint64_t)(dist + 1) * 8 + 31) / 32;
+  return (uint32_t)std::min<uint64_t>(PREFILTER_WORDS, std::max<uint64_t>(16, round_up(w, 16)));
+}
 constexpr size_t SWEEP_SMEM = (size_t)STAGES * 2 * STAGE_U4 * sizeof(uint4);
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
@@ -1387,22 +1393,23 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     bool refined = false;
     const bool try_prefilter = o.sweep_variant == 0 && o.dist >= 0 && (uint64_t)o.dist < (uint64_t)PREFILTER_WORDS * 32 &&
                                Wp >= 4 * PREFILTER_WORDS;
-    if (try_prefilter) {
-      a.Wp = PREFILTER_WORDS;
+    // narrow window first (a quarter of the work when it is enough), the widest one if too many pairs survive it
+    for (uint32_t pw = try_prefilter ? prefilter_words(o.dist) : 0; pw && !refined; pw = pw < PREFILTER_WORDS ? PREFILTER_WORDS : 0) {
+      a.Wp = pw;
       T.start();
       launch_tile_sweep(a, tc_ok, st);
       S.ms_sweep += T.stop();
-      S.swept_wordpairs += band_pairs[b] * PREFILTER_WORDS;
+      S.swept_wordpairs += band_pairs[b] * pw;
       const unsigned long long n_cand = read_counter();
       if (n_cand > cap) throw std::runtime_error("internal error: edge buffer overflow");
-      S.n_candidates += n_cand;
       if (n_cand * 25 <= band_pairs[b]) {  // <= 4 % survive: per-pair refinement is cheaper than tiles
         refined = true;
+        S.n_candidates += n_cand;
         TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
         if (n_cand) {
           T.start();
-          k_refine<<<(unsigned)((n_cand * 32 + 255) / 256), 256, 0, st>>>(keys.p, dv.p, n_cand, planesT.p, Wp, PREFILTER_WORDS, o.dist,
-                                                                       counter.p, keys2.p, dv2.p);
+          k_refine<<<(unsigned)((n_cand * 32 + 255) / 256), 256, 0, st>>>(keys.p, dv.p, n_cand, planesT.p, Wp, pw, o.dist, counter.p,
+                                                                       keys2.p, dv2.p);
           S.kernel_launches++;
           TRACS_CK(cudaGetLastError());
           S.ms_refine += T.stop();
@@ -1411,6 +1418,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
         std::swap(keys.p, keys2.p);  // survivors now in (keys, dv) like the plain sweep leaves them
         std::swap(dv.p, dv2.p);
       } else {
+        if (pw == PREFILTER_WORDS) S.n_candidates += n_cand;
         TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
       }
     }
