@@ -282,14 +282,15 @@ def run_sites(args, saved_stdout, torch, tracs_b200, dist_mod, device, rank, wor
         peak = tracs_b200.int_peak()
         peak_wp = min(peak["lop3_per_s"] / 4.0, peak["popc_per_s"])
         wp = avg("swept_wordpairs")
+        pf_words = int(round(wp / max(1.0, avg("n_pairs"))))
         t_sw = avg("ms_sweep") * 1e-3
         if avg("tc_sweep") > 0.5:
-            roof = {"bound": "tensor", "kernel": "k_sweep_tc", "what": "prefilter launch on this rank's row-blocks (first 64 local words), "
+            roof = {"bound": "tensor", "kernel": "k_sweep_tc", "what": "prefilter launch on this rank's row-blocks (first %d local words), " % pf_words +
                     "tcgen05 int8 one-hot GEMM", "achieved": 2 * wp * 32 * 4 / t_sw / 1e12, "peak": 4500.0, "unit": "TOP/s",
                     "frac": 2 * wp * 32 * 4 / t_sw / 1e12 / 4500.0, "traffic": None, "ms_per_launch": avg("ms_sweep"),
                     "peak_source": "NOMINAL dense int8 (4.5 POP/s)", "equivalent_int_pipe_frac": (wp / t_sw) / peak_wp}
         else:
-            roof = {"bound": "int_pipe", "kernel": "k_sweep", "what": "prefilter launch on this rank's row-blocks (first 64 local words)",
+            roof = {"bound": "int_pipe", "kernel": "k_sweep", "what": "prefilter launch on this rank's row-blocks (first %d local words)" % pf_words,
                     "achieved": wp * 6 / t_sw / 1e9, "peak": peak_wp * 6 / 1e9, "unit": "Ginstr/s", "frac": (wp / t_sw) / peak_wp,
                     "traffic": None, "ms_per_launch": avg("ms_sweep"), "peak_source": "measured in this run (tracs_int_peak)"}
         line = {
