@@ -276,21 +276,27 @@ bool read_fasta_parallel(const char *path, int n_threads, ByteBuf &ascii, std::v
 
   // 1. record starts: '>' at the start of a line
   std::vector<std::vector<size_t>> found((size_t)T);
+  std::atomic<int> scan_failed(0);
   {
     std::vector<std::thread> pool;
     for (int t = 0; t < T; ++t)
       pool.emplace_back([&, t] {
-        const size_t lo = m.size / T * t, hi = (t == T - 1) ? m.size : m.size / T * (t + 1);
-        const unsigned char *q = d + lo;
-        while (q < d + hi) {
-          q = static_cast<const unsigned char *>(memchr(q, '>', (size_t)(d + hi - q)));
-          if (!q) break;
-          if (q == d || q[-1] == '\n') found[t].push_back((size_t)(q - d));
-          ++q;
+        try {
+          const size_t lo = m.size / T * t, hi = (t == T - 1) ? m.size : m.size / T * (t + 1);
+          const unsigned char *q = d + lo;
+          while (q < d + hi) {
+            q = static_cast<const unsigned char *>(memchr(q, '>', (size_t)(d + hi - q)));
+            if (!q) break;
+            if (q == d || q[-1] == '\n') found[t].push_back((size_t)(q - d));
+            ++q;
+          }
+        } catch (...) {
+          scan_failed.store(1);
         }
       });
     for (auto &th : pool) th.join();
   }
+  if (scan_failed.load()) return false;
   std::vector<size_t> starts;
   for (auto &v : found) starts.insert(starts.end(), v.begin(), v.end());
   const size_t R = starts.size();  // >= 1
@@ -343,15 +349,19 @@ bool read_fasta_parallel(const char *path, int n_threads, ByteBuf &ascii, std::v
     uint8_t *out0 = ascii.data() + base;
     for (int t = 0; t < T; ++t)
       pool.emplace_back([&] {
-        for (;;) {
-          const size_t r = next.fetch_add(1);
-          if (r >= n_par || not_simple.load(std::memory_order_relaxed)) break;
-          uint64_t nb = 0;
-          if (!parse_simple_record(d + starts[r], d + starts[r + 1], par_names[r], out0 + r * L, L, nb)) {
-            not_simple.store(1);
-            break;
+        try {
+          for (;;) {
+            const size_t r = next.fetch_add(1);
+            if (r >= n_par || not_simple.load(std::memory_order_relaxed)) break;
+            uint64_t nb = 0;
+            if (!parse_simple_record(d + starts[r], d + starts[r + 1], par_names[r], out0 + r * L, L, nb)) {
+              not_simple.store(1);
+              break;
+            }
+            if (nb != L) bad_len.store(1);
           }
-          if (nb != L) bad_len.store(1);
+        } catch (...) {  // out of memory while storing a name: let the sequential reader report it
+          not_simple.store(1);
         }
       });
     for (auto &th : pool) th.join();
