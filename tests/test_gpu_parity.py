@@ -225,6 +225,26 @@ def test_recombination_filter(oracle_mod):
         assert (f < d).any() and res["ncomp"].tolist() == nn.tolist()
 
 
+def test_recombination_filter_on_early_extraction_ingest(oracle_mod, monkeypatch):
+    """The filter walks each pair's SNP positions in ascending order: the planes built by the early-extraction ingest
+    (early list merged with late sites) must keep that order. n > 256 so that the path can be forced."""
+    s = synth.generate(300, 40_000, p_var=0.02, n_clusters=30, mu=6, p_N=0.002, p_amb=0.01, seed=52)
+    rng = np.random.default_rng(3)
+    for k in range(0, 300, 7):
+        start = int(rng.integers(1000, 39000))
+        sites = start + rng.choice(400, size=30, replace=False)
+        s[k, sites] = np.where(s[k, sites] == ord("A"), ord("C"), ord("A"))
+    for c in rng.integers(0, 40_000, size=30):      # sites that only vary after the first 256 samples
+        s[:, c] = ord("G")
+        s[rng.integers(256, 300), c] = ord("T")
+    monkeypatch.setenv("TRACS_INGEST", "early")
+    res = tracs_b200.pairsnp_matrix(s, dist=150, filter=True)
+    assert tracs_b200.last_stats()["n_early_sites"] > 0
+    r, c, d, f, nn = oracle_mod.pairsnp_ascii(s, dist=150, filter=True, n_threads=8)
+    assert res["rows"].tolist() == r.tolist() and res["cols"].tolist() == c.tolist() and res["dist"].tolist() == d.tolist()
+    assert res["filt"].tolist() == f.tolist() and (f < d).any() and res["ncomp"].tolist() == nn.tolist()
+
+
 def test_filter_golden_and_fused_trans(oracle_mod):
     import json
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
