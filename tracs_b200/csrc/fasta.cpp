@@ -9,6 +9,7 @@
 //   * all records of one file must have equal length (src/pairsnp.hpp:94-98).
 // Plain files are parsed by n_threads workers (read_fasta_parallel below) when that is provably the same.
 #include <emmintrin.h>
+#include <immintrin.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -32,6 +33,36 @@ namespace {
 enum State { SEEK, NAME, REST_OF_HEADER, SEQ, PLUS_LINE, QUAL, QUAL_TRAIL };
 
 inline bool is_space(unsigned c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+// 32 bytes at a time where the CPU has AVX2 (run-time check; the SSE2 / scalar code below it handles whatever is
+// left). Copies sequence bytes from p to o, dropping non-printable ones; returns at a record delimiter ('>', '@',
+// '+'), which is left for the caller, or when fewer than 32 input bytes / 32 bytes of room (o_end, may be null =
+// unlimited) remain. Every store writes 32 bytes at o, of which only the clean prefix is kept.
+__attribute__((target("avx2"))) void bulk_copy_avx2(const unsigned char *&p, const unsigned char *end, uint8_t *&o, const uint8_t *o_end) {
+  const __m256i c_gt = _mm256_set1_epi8('>'), c_at = _mm256_set1_epi8('@'), c_pl = _mm256_set1_epi8('+');
+  const __m256i c33 = _mm256_set1_epi8(33), c126 = _mm256_set1_epi8(126);
+  while (end - p >= 32 && (!o_end || o_end - o >= 32)) {
+    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+    const __m256i ok_lo = _mm256_cmpeq_epi8(_mm256_max_epu8(v, c33), v);   // v >= 33
+    const __m256i ok_hi = _mm256_cmpeq_epi8(_mm256_min_epu8(v, c126), v);  // v <= 126
+    const __m256i delim = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, c_gt), _mm256_cmpeq_epi8(v, c_at)), _mm256_cmpeq_epi8(v, c_pl));
+    const __m256i good = _mm256_andnot_si256(delim, _mm256_and_si256(ok_lo, ok_hi));
+    const unsigned bad = ~(unsigned)_mm256_movemask_epi8(good);
+    _mm256_storeu_si256(reinterpret_cast<__m256i *>(o), v);
+    if (!bad) {
+      o += 32;
+      p += 32;
+      continue;
+    }
+    const unsigned k = (unsigned)__builtin_ctz(bad);
+    o += k;
+    p += k;
+    const unsigned c = *p;
+    if (c == '>' || c == '@' || c == '+') return;
+    ++p;  // a dropped byte (newline, CR, blank, ...)
+  }
+}
+const bool g_have_avx2 = __builtin_cpu_supports("avx2") != 0;
 }  // namespace
 
 // The sequential reader: a state machine fed with consecutive byte ranges of the (decompressed) file.
@@ -90,13 +121,17 @@ struct FastaMachine {
         case SEQ: {
           // Bulk copy of sequence bytes, 16 at a time (SSE2). A byte is "special" if it ends the
           // sequence ('>', '@', '+') or is not printable (newline, CR, space, ...): those are dropped.
-          ascii.reserve(len + (size_t)(end - p) + 16);
+          ascii.reserve(len + (size_t)(end - p) + 32);
           uint8_t *o = ascii.data() + len;
           const __m128i c_gt = _mm_set1_epi8('>'), c_at = _mm_set1_epi8('@'), c_pl = _mm_set1_epi8('+');
           const __m128i c33 = _mm_set1_epi8(33), c126 = _mm_set1_epi8(126);
           bool ended = false;
           unsigned endc = 0;
           while (p < end) {
+            if (g_have_avx2) {
+              bulk_copy_avx2(p, end, o, nullptr);
+              if (p >= end) break;
+            }
             if (end - p >= 16) {
               const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
               const __m128i ok_lo = _mm_cmpeq_epi8(_mm_max_epu8(v, c33), v);    // v >= 33
@@ -215,6 +250,10 @@ bool parse_simple_record(const unsigned char *p, const unsigned char *end, std::
   const __m128i c_gt = _mm_set1_epi8('>'), c_at = _mm_set1_epi8('@'), c_pl = _mm_set1_epi8('+');
   const __m128i c33 = _mm_set1_epi8(33), c126 = _mm_set1_epi8(126);
   while (p < end) {
+    if (g_have_avx2 && out) {
+      bulk_copy_avx2(p, end, o, o_end);
+      if (p >= end) break;
+    }
     if (end - p >= 16 && o_end - o >= 16) {  // the 16-byte store must stay inside this record's slot
       const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
       const __m128i ok_lo = _mm_cmpeq_epi8(_mm_max_epu8(v, c33), v);
