@@ -45,8 +45,9 @@ typedef struct tracs_edges {
   char **names;      /* n_names NUL-terminated strings, or NULL           */
   uint64_t seq_length;
   /* tracs_opts_t.keep_on_device: the same columns, still in DEVICE memory, packed column-wise as
-   * u32 rows[n] | u32 cols[n] | u32 dist (filt if filter) [n] | u32 ncomp[n] | f64 p0_log[n] | f64 eK[n]
-   * (32 bytes per edge) so a multi-GPU caller can gather edge lists GPU-to-GPU. NULL otherwise. */
+   * u32 rows[n] | u32 cols[n] | u32 dist[n] (the raw SNP distance) | u32 ncomp[n] | f64 p0_log[n] | f64 eK[n]
+   * (32 bytes per edge) so a multi-GPU caller can gather edge lists GPU-to-GPU. The filtered distance is not
+   * part of the block (callers that ran the filter gather the host columns). NULL otherwise. */
   void *dev_packed;
   size_t dev_packed_bytes;
 } tracs_edges_t;
@@ -94,6 +95,9 @@ typedef struct tracs_opts {
                           * tile sweep; 2 = full-length sweep on the tensor cores (tcgen05 int8 one-hot GEMM; needs
                           * single-base-or-N masks at the variable sites, else the call fails) */
   int32_t keep_on_device; /* also return the edge columns packed in device memory (tracs_edges_t.dev_packed) */
+  int32_t packed_input;   /* the alignment is given as 4-bit base masks, two sites per byte (see tracs_pairsnp_packed),
+                           * instead of ASCII: applies to tracs_pairsnp_host / _device and tracs_site_shard_open */
+  int32_t reserved0;
 } tracs_opts_t;
 
 /* Replaces TRACS.pairsnp(fasta, n_threads, dist, filter) -- src/python_bindings.cpp:12-13,
@@ -113,6 +117,18 @@ int tracs_pairsnp_host(const uint8_t *seqs, size_t n, size_t L, size_t pitch, co
 /* Same, with the ASCII matrix already resident in DEVICE memory (pitch % 16 == 0). */
 int tracs_pairsnp_device(const uint8_t *dev_seqs, size_t n, size_t L, size_t pitch, const tracs_opts_t *opts,
                          tracs_edges_t *out);
+
+/* Same sweep on an alignment held in DEVICE memory as 4-bit base masks: nib[n][pitch_bytes], site s of a sample in
+ * byte s >> 1, bits [4 * (s & 1), +4); the nibble is the mask the reference's loader derives from the base
+ * (src/pairsnp.hpp:107-199: bit0 A, bit1 C, bit2 G, bit3 T; N, '-', anything else = 1111). pitch_bytes % 16 == 0 and
+ * 2 * pitch_bytes >= L rounded up to 32. Half the bytes of the ASCII matrix: 100 000 x 2 Mb is 100 GB and fits one
+ * B200 (SURVEY 8b `tracs_pairsnp_packed`, 8d "packed 4-bit IUPAC masks directly on device"). */
+int tracs_pairsnp_packed(const uint8_t *dev_nib, size_t n, size_t L, size_t pitch_bytes, const tracs_opts_t *opts,
+                         tracs_edges_t *out);
+
+/* ASCII rows -> packed rows on the device (what the host-streaming path runs per chunk): dev_ascii[rows][pitch]
+ * (pitch % 32 == 0, >= L rounded up to 32) -> dev_nib[rows][pitch_bytes]. Sites >= L become 1111. */
+int tracs_encode_packed(const uint8_t *dev_ascii, size_t rows, size_t L, size_t pitch, uint8_t *dev_nib, size_t pitch_bytes);
 
 void tracs_edges_free(tracs_edges_t *e);
 
@@ -163,6 +179,13 @@ int tracs_min_over_refs(const uint64_t *a, const uint64_t *b, const double *val,
 int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size_t pitch, const tracs_opts_t *opts,
                           void **handle, const uint64_t **dev_cand_keys, size_t *n_cand);
 int tracs_site_shard_partials(void *handle, const uint64_t *dev_keys, size_t n_keys, uint32_t *dev_d, uint32_t *dev_union);
+/* Last step of the site-sharded sweep, on ONE rank (the all-reduce leaves every rank with the summed vectors):
+ * keeps the candidates with d <= opts->dist, compared sites = L_total - union, optional fused transmission
+ * likelihood (opts->days of all n samples), columns to page-locked host memory. dev_keys sorted ascending
+ * (i << 32 | j), dev_d / dev_union: the summed per-candidate vectors. `handle` may be NULL (nothing of the
+ * shard is read). Output as tracs_pairsnp_device. */
+int tracs_site_shard_finish(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, size_t n_keys,
+                            size_t n_samples, size_t L_total, const tracs_opts_t *opts, tracs_edges_t *out);
 int tracs_site_shard_close(void *handle);
 
 /* Single-linkage clusters of the thresholded edge list = connected components (what tracs/cluster.py:126-129
@@ -205,6 +228,8 @@ typedef struct tracs_synth {
   uint32_t gaps;   /* number of '-' runs of length L/1000 per sample     */
   uint64_t site_offset; /* generate columns [site_offset, site_offset + L) of an alignment of L_total sites */
   uint64_t L_total;     /* 0 = L (whole alignment)                                                        */
+  uint32_t packed;      /* 1: write 4-bit masks (tracs_pairsnp_packed layout), `pitch` = bytes per packed row */
+  uint32_t reserved0;
 } tracs_synth_t;
 int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev_days);
 
@@ -221,6 +246,12 @@ int tracs_memcpy_h2d(void *dst, const void *src, size_t bytes);
  * out[3] = word-pairs/s of the sweep's (4 LOP3 + POPC + ADD) mix, out[4] = same with the add
  * issued as IMAD (FMA pipe), out[5] = SM count. */
 int tracs_int_peak(double out[8]);
+
+/* Measures the int8 tensor-pipe peak on the current device: every SM issues back-to-back
+ * tcgen05.mma.cta_group::1.kind::i8 (M = 128, K = 32) from shared-memory operands into TMEM.
+ * out[0] = TOP/s with N = 128 (the shape k_sweep_tc issues), out[1] = TOP/s with N = 256,
+ * out[2], out[3] = SM clock cycles per MMA for the two shapes. */
+int tracs_tc_peak(double out[4]);
 
 #ifdef __cplusplus
 }

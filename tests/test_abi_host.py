@@ -29,12 +29,25 @@ def test_exports_match_header():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
 
 
-def test_struct_layouts_match_c():
-    # sizes the C compiler gives for the structs in include/tracs_b200.h (x86-64 SysV)
-    assert C.sizeof(_lib.Edges) == 14 * 8
-    assert C.sizeof(_lib.Stats) == 13 * 8 + 12 * 4
-    assert C.sizeof(_lib.Opts) == 8 + 16 + 16 + 8 + 24 + 8
-    assert C.sizeof(_lib.Synth) == 32 + 8 + 8 + 32 + 8 + 16
+def test_struct_layouts_match_c(tmp_path):
+    """sizeof / offsetof of every struct in include/tracs_b200.h as gcc lays them out == the ctypes mirrors."""
+    import subprocess
+    structs = {"tracs_edges_t": _lib.Edges, "tracs_stats_t": _lib.Stats, "tracs_opts_t": _lib.Opts, "tracs_synth_t": _lib.Synth}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tracs_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, f)]) == getattr(cls, f).offset, (cname, f)
 
 
 def test_no_gpu_fails_loudly():

@@ -6,8 +6,9 @@ resolve to it, so the reference's tracs/distance.py, tracs/transcluster.py run u
 import os
 import sys
 
-from .api import (pairsnp, trans_dist, lprob_k_given_N, calculate_posteriors, pairsnp_matrix, pairsnp_device,
-                  min_over_refs, synth_device, int_peak, last_stats, read_fasta, shard_rowblocks, connected_components, INT32_MAX)
+from .api import (pairsnp, trans_dist, lprob_k_given_N, calculate_posteriors, pairsnp_matrix, pairsnp_device, pairsnp_packed,
+                  pairsnp_packed_host, pack_nibbles,
+                  min_over_refs, synth_device, int_peak, tc_peak, last_stats, read_fasta, shard_rowblocks, connected_components, INT32_MAX)
 
 DROPIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
 

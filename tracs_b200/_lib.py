@@ -35,13 +35,15 @@ class Opts(C.Structure):
     _fields_ = [("dist", C.c_int32), ("filter", C.c_int32), ("i_end", C.c_uint64), ("j_start", C.c_uint64),
                 ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("want_ncomp", C.c_int32),
                 ("want_trans", C.c_int32), ("days", C.POINTER(C.c_int32)), ("lamb", C.c_double), ("beta", C.c_double),
-                ("threshold_Ek", C.c_double), ("sweep_variant", C.c_int32), ("keep_on_device", C.c_int32)]
+                ("threshold_Ek", C.c_double), ("sweep_variant", C.c_int32), ("keep_on_device", C.c_int32),
+                ("packed_input", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class Synth(C.Structure):
     _fields_ = [("n", C.c_uint64), ("L", C.c_uint64), ("pitch", C.c_uint64), ("seed", C.c_uint64), ("p_var", C.c_double),
                 ("n_clusters", C.c_uint32), ("mu", C.c_double), ("p_N", C.c_double), ("p_amb", C.c_double),
-                ("gc", C.c_double), ("n_days", C.c_uint32), ("gaps", C.c_uint32), ("site_offset", C.c_uint64), ("L_total", C.c_uint64)]
+                ("gc", C.c_double), ("n_days", C.c_uint32), ("gaps", C.c_uint32), ("site_offset", C.c_uint64), ("L_total", C.c_uint64),
+                ("packed", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 # every symbol include/tracs_b200.h declares
@@ -51,7 +53,7 @@ SYMBOLS = ["tracs_pairsnp", "tracs_pairsnp_host", "tracs_pairsnp_device", "tracs
            "tracs_dev_free", "tracs_host_alloc_pinned", "tracs_host_free_pinned", "tracs_memcpy_d2h",
            "tracs_memcpy_h2d", "tracs_int_peak", "tracs_read_fasta", "tracs_free_fasta", "tracs_shard_rowblocks",
            "tracs_site_shard_open", "tracs_site_shard_partials", "tracs_site_shard_close", "tracs_connected_components",
-           "tracs_write_distance_csv", "tracs_float_repr"]
+           "tracs_write_distance_csv", "tracs_float_repr", "tracs_pairsnp_packed", "tracs_encode_packed", "tracs_site_shard_finish", "tracs_tc_peak"]
 
 _lib = None
 
@@ -66,6 +68,10 @@ def lib():
         L.tracs_pairsnp.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int32, C.c_int, C.POINTER(Edges)]
         L.tracs_pairsnp_host.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Opts), C.POINTER(Edges)]
         L.tracs_pairsnp_device.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Opts), C.POINTER(Edges)]
+        L.tracs_pairsnp_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Opts), C.POINTER(Edges)]
+        L.tracs_encode_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.tracs_site_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Opts),
+                                              C.POINTER(Edges)]
         L.tracs_edges_free.argtypes = [C.POINTER(Edges)]
         L.tracs_edges_free.restype = None
         L.tracs_trans_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
@@ -82,6 +88,7 @@ def lib():
         L.tracs_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.tracs_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.tracs_int_peak.argtypes = [C.c_void_p]
+        L.tracs_tc_peak.argtypes = [C.c_void_p]
         L.tracs_read_fasta.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                        C.POINTER(C.POINTER(C.c_char_p))]
         L.tracs_free_fasta.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_char_p), C.c_size_t]

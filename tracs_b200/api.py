@@ -70,7 +70,7 @@ def calculate_posteriors(counts, alphas, keep, threshold):
 # ---- extras (not in the reference module) ------------------------------------------------------
 
 def make_opts(dist=INT32_MAX, i_end=0, j_start=0, shard_rank=0, shard_world=1, want_ncomp=True, days=None, lamb=29.903,
-              beta=73.0, threshold_Ek=0.01, filter=False, full_sweep=False, keep_on_device=False):
+              beta=73.0, threshold_Ek=0.01, filter=False, full_sweep=False, keep_on_device=False, packed=False):
     o = Opts()
     o.dist = int(dist)
     o.filter = int(bool(filter))
@@ -81,6 +81,7 @@ def make_opts(dist=INT32_MAX, i_end=0, j_start=0, shard_rank=0, shard_world=1, w
     o.want_ncomp = int(bool(want_ncomp))
     o.sweep_variant = 2 if full_sweep == "tc" else (1 if full_sweep else 0)
     o.keep_on_device = int(bool(keep_on_device))
+    o.packed_input = int(bool(packed))
     keep = None
     if days is not None:
         keep = np.ascontiguousarray(days, dtype=np.int32)
@@ -109,6 +110,41 @@ def pairsnp_device(dev_ptr, n, L, pitch, copy=True, **kw):
     return _lib.take_edges(e, names=False, copy=copy)
 
 
+MASKS = np.full(256, 15, np.uint8)
+for _c, _m in zip("ACGTMRWSYKVHDB", (1, 2, 4, 8, 3, 5, 9, 6, 10, 12, 7, 11, 13, 14)):
+    MASKS[ord(_c)] = MASKS[ord(_c.lower())] = _m
+
+
+def pack_nibbles(seqs):
+    """Host helper: ASCII matrix uint8[n][L] -> 4-bit packed rows uint8[n][pitch] in the layout
+    tracs_pairsnp_packed takes (site s in byte s >> 1, low nibble first; pitch a multiple of 16 bytes holding L rounded
+    up to 32 sites; padding sites = 1111). The nibble is the base mask of src/pairsnp.hpp:107-199."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    n, L = seqs.shape
+    pitch = max(16, (L + 31) // 32 * 16)
+    m = np.full((n, pitch * 2), 15, np.uint8)
+    m[:, :L] = MASKS[seqs]
+    return (m[:, 0::2] | (m[:, 1::2] << 4)).astype(np.uint8), pitch
+
+
+def pairsnp_packed_host(nib, L, copy=True, **kw):
+    """Pair sweep on a HOST matrix of 4-bit packed rows (pack_nibbles layout); H2D copy included."""
+    nib = np.ascontiguousarray(nib, dtype=np.uint8)
+    n, pitch = nib.shape
+    o, keep = make_opts(packed=True, **kw)
+    e = Edges()
+    _lib.check(_lib.lib().tracs_pairsnp_host(nib.ctypes.data, n, L, pitch, C.byref(o), C.byref(e)))
+    return _lib.take_edges(e, names=False, copy=copy)
+
+
+def pairsnp_packed(dev_ptr, n, L, pitch_bytes, copy=True, **kw):
+    """Pair sweep on a DEVICE-resident 4-bit packed alignment (raw device pointer as int)."""
+    o, keep = make_opts(**kw)
+    e = Edges()
+    _lib.check(_lib.lib().tracs_pairsnp_packed(C.c_void_p(dev_ptr), n, L, pitch_bytes, C.byref(o), C.byref(e)))
+    return _lib.take_edges(e, names=False, copy=copy)
+
+
 def min_over_refs(a, b, val):
     """Min-over-references combine: unordered (a,b) -> min(val). Sorted by (lo, hi)."""
     a = np.ascontiguousarray(a, dtype=np.uint64)
@@ -125,11 +161,12 @@ def min_over_refs(a, b, val):
 
 
 def synth_device(dev_ptr, n, L, pitch, seed=1, p_var=0.01, n_clusters=20, mu=5.0, p_N=1e-3, p_amb=0.0, gc=0.5, n_days=180,
-                 gaps=2, dev_days=None, site_offset=0, L_total=0):
+                 gaps=2, dev_days=None, site_offset=0, L_total=0, packed=False):
     """Seeded synthetic alignment written straight into device memory. With site_offset / L_total the
     buffer receives the column slab [site_offset, site_offset + L) of an L_total-site alignment
-    (identical bytes to the corresponding columns of the whole alignment)."""
-    cfg = _lib.Synth(n, L, pitch, seed, p_var, n_clusters, mu, p_N, p_amb, gc, n_days, gaps, site_offset, L_total)
+    (identical bytes to the corresponding columns of the whole alignment). packed=True writes 4-bit masks
+    (tracs_pairsnp_packed layout; `pitch` = bytes per packed row) of the same alignment."""
+    cfg = _lib.Synth(n, L, pitch, seed, p_var, n_clusters, mu, p_N, p_amb, gc, n_days, gaps, site_offset, L_total, int(bool(packed)), 0)
     _lib.check(_lib.lib().tracs_synth_device(C.byref(cfg), C.c_void_p(dev_ptr), C.c_void_p(dev_days) if dev_days else None))
 
 
@@ -173,6 +210,15 @@ def int_peak():
     _lib.check(_lib.lib().tracs_int_peak(out.ctypes.data))
     return {"lop3_per_s": out[0], "popc_per_s": out[1], "iadd_per_s": out[2], "mix_wordpairs_per_s": out[3],
             "mix_imad_wordpairs_per_s": out[4], "n_sm": int(out[5])}
+
+
+def tc_peak():
+    """Measured int8 tensor-pipe peak (tracs_tc_peak): back-to-back tcgen05.mma kind::i8 on every SM."""
+    out = np.zeros(4, np.float64)
+    _lib.check(_lib.lib().tracs_tc_peak(out.ctypes.data))
+    return {"tops": float(max(out[0], out[1])), "tops_n128": float(out[0]), "tops_n256": float(out[1]), "clk_per_mma_n128": float(out[2]),
+            "clk_per_mma_n256": float(out[3]),
+            "source": "measured in this run (tracs_tc_peak: back-to-back tcgen05.mma kind::i8 M128 K32 on all SMs, N = 128 / 256, best shape)"}
 
 
 def last_stats():

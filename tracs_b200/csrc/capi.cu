@@ -226,9 +226,10 @@ struct SynthDev {
   uint32_t thr_priv32, thr_N32, thr_amb16, n_days, gaps;
   uint64_t gap_len;
   uint64_t site_offset, L_total;  // this buffer holds columns [site_offset, site_offset + L) of L_total
+  uint32_t packed;                // write 4-bit masks (two sites per byte) instead of ASCII
 };
 __global__ void k_synth(SynthDev c, uint8_t *__restrict__ seqs) {
-  const uint64_t chunks = c.pitch / 16;
+  const uint64_t chunks = (c.packed ? c.pitch * 2 : c.pitch) / 16;  // 16 sites per thread
   const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= c.n * chunks) return;
   const uint64_t s = gid / chunks, ch = gid % chunks;
@@ -240,6 +241,7 @@ __global__ void k_synth(SynthDev c, uint8_t *__restrict__ seqs) {
   // 2-base IUPAC codes indexed [b][o]
   const char AMB[4][4] = {{'A', 'M', 'R', 'W'}, {'M', 'C', 'S', 'Y'}, {'R', 'S', 'G', 'K'}, {'W', 'Y', 'K', 'T'}};
   uint32_t outw[4];
+  uint32_t nibw[2] = {0u, 0u};
   for (int q = 0; q < 4; ++q) {
     uint32_t w = 0;
     for (int t = 0; t < 4; ++t) {
@@ -266,10 +268,12 @@ __global__ void k_synth(SynthDev c, uint8_t *__restrict__ seqs) {
         for (int r = 0; r < 4; ++r) if (site >= g0[r] && site - g0[r] < c.gap_len) chv = '-';
       }
       w |= (uint32_t)(uint8_t)chv << (8 * t);
+      nibw[q >> 1] |= base_mask((uint32_t)(uint8_t)chv) << (4 * ((q & 1) * 4 + t));
     }
     outw[q] = w;
   }
-  *reinterpret_cast<uint4 *>(seqs + s * c.pitch + ch * 16) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+  if (c.packed) *reinterpret_cast<uint2 *>(seqs + s * c.pitch + ch * 8) = make_uint2(nibw[0], nibw[1]);
+  else *reinterpret_cast<uint4 *>(seqs + s * c.pitch + ch * 16) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
 }
 __global__ void k_synth_days(uint64_t n, uint64_t seed, uint32_t n_days, int32_t *days) {
   uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,6 +448,91 @@ static void h2d_rows(uint8_t *dev, size_t dpitch, const uint8_t *src, size_t spi
   (void)st;  // the workers have synchronised their streams: the data is in place for any stream
 }
 
+// Host matrix -> device-resident PACKED alignment (pack4.inl layout), streamed in sample chunks: the copy of chunk
+// c + 1 (copy stream) overlaps the ASCII -> nibble encode of chunk c (compute stream), and only two ASCII chunks are
+// ever resident, so an alignment whose ASCII form exceeds the device (100 000 x 2 Mb = 200 GB) still goes through.
+// A host matrix that is already packed is copied straight into place.
+static void stream_host_to_packed(const uint8_t *seqs, size_t n, size_t L, size_t hpitch, bool host_is_packed, DevBuf<uint8_t> &nib,
+                                  size_t &pitch4, cudaStream_t st) {
+  pitch4 = std::max<size_t>(16, (L + 31) / 32 * 16);
+  nib.alloc(n * pitch4);
+  if (n == 0 || L == 0) return;
+  if (host_is_packed) {
+    h2d_rows(nib.p, pitch4, seqs, hpitch, (L + 1) / 2, n, st);
+    g_stats.h2d_bytes += (uint64_t)n * ((L + 1) / 2);
+    return;
+  }
+  const size_t apitch = (L + 31) / 32 * 32;
+  const char *env_ch = getenv("TRACS_STREAM_CHUNK_BYTES");  // tests shrink it to exercise many chunks
+  const size_t chunk_bytes = env_ch ? (size_t)strtoull(env_ch, nullptr, 10) : ((size_t)256 << 20);
+  const size_t R = std::min(n, std::max<size_t>(1, chunk_bytes / apitch));
+  DevBuf<uint8_t> stage0(R * apitch), stage1(n > R ? R * apitch : 0);
+  uint8_t *stage[2] = {stage0.p, stage1.p ? stage1.p : stage0.p};
+  static thread_local cudaStream_t cp = nullptr;
+  static thread_local cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  static thread_local int cp_dev = -1;
+  int dev = 0;
+  TRACS_CK(cudaGetDevice(&dev));
+  if (!cp || cp_dev != dev) {
+    cp_dev = dev;
+    TRACS_CK(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      TRACS_CK(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+      TRACS_CK(cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming));
+    }
+  }
+  size_t c = 0;
+  for (size_t r0 = 0; r0 < n; r0 += R, ++c) {
+    const int b = (int)(c & 1);
+    const size_t nr = std::min(R, n - r0);
+    if (c >= 2) TRACS_CK(cudaStreamWaitEvent(cp, ev_free[b], 0));  // the encode that last read this buffer is done
+    h2d_rows(stage[b], apitch, seqs + r0 * hpitch, hpitch, L, nr, cp);
+    TRACS_CK(cudaEventRecord(ev_copied[b], cp));
+    TRACS_CK(cudaStreamWaitEvent(st, ev_copied[b], 0));
+    encode_rows_device(stage[b], nr, L, apitch, nib.p + r0 * pitch4, pitch4, st);
+    TRACS_CK(cudaEventRecord(ev_free[b], st));
+  }
+  TRACS_CK(cudaStreamSynchronize(st));  // the staging buffers go back to the cache
+  g_stats.h2d_bytes += (uint64_t)n * L;
+}
+
+int tracs_encode_packed(const uint8_t *dev_ascii, size_t rows, size_t L, size_t pitch, uint8_t *dev_nib, size_t pitch_bytes) {
+  return guarded([&] {
+    require_device();
+    encode_rows_device(dev_ascii, rows, L, pitch, dev_nib, pitch_bytes, 0);
+    TRACS_CK(cudaStreamSynchronize(0));
+  });
+}
+
+int tracs_pairsnp_packed(const uint8_t *dev_nib, size_t n, size_t L, size_t pitch_bytes, const tracs_opts_t *opts,
+                         tracs_edges_t *out) {
+  memset(out, 0, sizeof *out);
+  memset(&g_stats, 0, sizeof g_stats);
+  return guarded([&] {
+    require_device();
+    tracs_opts_t o = normalise(opts, n);
+    o.packed_input = 1;
+    HostEdges he;
+    sweep_device(dev_nib, n, L, pitch_bytes, o, he, 0);
+    finish_edges(he, o, n, L, out, 0);
+  });
+}
+
+int tracs_site_shard_finish(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, size_t n_keys,
+                            size_t n_samples, size_t L_total, const tracs_opts_t *opts, tracs_edges_t *out) {
+  memset(out, 0, sizeof *out);
+  memset(&g_stats, 0, sizeof g_stats);
+  return guarded([&] {
+    require_device();
+    if (!opts) throw std::runtime_error("site shard: options required");
+    tracs_opts_t o = normalise(opts, n_samples);
+    o.filter = 0;
+    HostEdges he;
+    site_shard_finish_device(dev_keys, dev_d, dev_union, n_keys, n_samples, L_total, o, he, 0);
+    finish_edges(he, o, n_samples, L_total, out, 0);
+  });
+}
+
 int tracs_pairsnp_device(const uint8_t *dev_seqs, size_t n, size_t L, size_t pitch, const tracs_opts_t *opts,
                          tracs_edges_t *out) {
   memset(out, 0, sizeof *out);
@@ -465,13 +554,20 @@ int tracs_pairsnp_host(const uint8_t *seqs, size_t n, size_t L, size_t pitch, co
     require_device();
     tracs_opts_t o = normalise(opts, n);
     HostEdges he;
-    if (n > 0) {
+    const char *mode = getenv("TRACS_HOST_INGEST");  // "ascii": keep the ASCII matrix resident and pack it directly
+    if (n > 0 && !o.packed_input && mode && !strcmp(mode, "ascii")) {
       const size_t dp = std::max<size_t>(32, (L + 31) / 32 * 32);
       DevBuf<uint8_t> d(n * dp);
       if (dp != L) TRACS_CK(cudaMemsetAsync(d.p, 'N', n * dp, 0));
       if (L > 0) h2d_rows(d.p, dp, seqs, pitch, L, n, 0);
       sweep_device(d.p, n, L, dp, o, he, 0);
       g_stats.h2d_bytes += (uint64_t)n * L;
+    } else if (n > 0) {
+      DevBuf<uint8_t> nib;
+      size_t pitch4 = 0;
+      stream_host_to_packed(seqs, n, L, pitch, o.packed_input != 0, nib, pitch4, 0);
+      o.packed_input = 1;
+      sweep_device(nib.p, n, L, pitch4, o, he, 0);  // adds to the counters of the call
     }
     finish_edges(he, o, n, L, out, 0);
   });
@@ -846,8 +942,10 @@ int tracs_write_distance_csv(const char *path, int append, const tracs_edges_t *
 int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev_days) {
   return guarded([&] {
     require_device();
-    if (cfg->pitch % 16 != 0 || cfg->pitch < cfg->L) throw std::runtime_error("synth: pitch must be a multiple of 16 and >= L");
+    if (!cfg->packed && (cfg->pitch % 16 != 0 || cfg->pitch < cfg->L)) throw std::runtime_error("synth: pitch must be a multiple of 16 and >= L");
+    if (cfg->packed && (cfg->pitch % 16 != 0 || cfg->pitch * 2 < cfg->L)) throw std::runtime_error("synth: packed pitch must be a multiple of 16 bytes and hold L sites");
     SynthDev c;
+    c.packed = cfg->packed ? 1u : 0u;
     c.n = cfg->n; c.L = cfg->L; c.pitch = cfg->pitch; c.seed = cfg->seed;
     auto clamp01 = [](double x) { return x < 0 ? 0.0 : (x > 1 ? 1.0 : x); };
     c.thr_var24 = (uint32_t)(clamp01(cfg->p_var) * 16777216.0);
@@ -863,7 +961,7 @@ int tracs_synth_device(const tracs_synth_t *cfg, uint8_t *dev_seqs, int32_t *dev
     c.thr_amb16 = (uint32_t)(clamp01(cfg->p_amb) * 65536.0);
     c.n_days = cfg->n_days; c.gaps = cfg->gaps;
     c.gap_len = c.L_total / 1000;
-    const uint64_t total = c.n * (c.pitch / 16);
+    const uint64_t total = c.n * ((c.packed ? c.pitch * 2 : c.pitch) / 16);
     if (total) {
       k_synth<<<(unsigned)((total + 255) / 256), 256>>>(c, dev_seqs);
       TRACS_CK(cudaGetLastError());

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <memory>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -102,6 +103,35 @@ struct Timer {
     return ms;
   }
 };
+
+// ------------------------------------------------------------------------------------------
+// base-mask table: bit0=A bit1=C bit2=G bit3=T ; everything that is not an IUPAC code = 15
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t base_mask(uint32_t c) {
+  c &= 0xFFu;
+  if (c >= 'a' && c <= 'z') c -= 32;
+  switch (c) {
+    case 'A': return 1;
+    case 'C': return 2;
+    case 'G': return 4;
+    case 'T': return 8;
+    case 'M': return 3;
+    case 'R': return 5;
+    case 'W': return 9;
+    case 'S': return 6;
+    case 'Y': return 10;
+    case 'K': return 12;
+    case 'V': return 7;
+    case 'H': return 11;
+    case 'D': return 13;
+    case 'B': return 14;
+    default: return 15;
+  }
+}
+
+// ASCII rows -> 4-bit packed rows on the device (pack4.inl, k_encode)
+void encode_rows_device(const uint8_t *dev_ascii, uint64_t rows, uint64_t L, uint64_t pitch, uint8_t *dev_nib, uint64_t pitch4,
+                        cudaStream_t st);
 
 // ---- geometry of the pair sweep ------------------------------------------------------------
 constexpr int TILE = 128;  // samples per tile side
@@ -201,9 +231,13 @@ struct HostEdges {
   size_t dev_packed_bytes = 0;
   ~HostEdges() { if (dev_packed) cudaFree(dev_packed); }
 };
-const std::vector<double> &lgamma_table(size_t n);
+std::shared_ptr<const std::vector<double>> lgamma_table(size_t n);  // lg[x] = lgamma(x), x < n; immutable snapshot
 void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,
                   HostEdges &out, cudaStream_t st);
+
+// last step of the site-sharded sweep (shard.inl): summed candidate vectors -> edge columns
+void site_shard_finish_device(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
+                              uint64_t L_total, const tracs_opts_t &o, HostEdges &out, cudaStream_t st);
 
 // transcluster on device (trans.cu)
 void trans_dist_device(const int32_t *snp, const double *dt, size_t n, double lamb, double beta, double thr,

@@ -62,6 +62,83 @@ k_shard_partials(const uint64_t *__restrict__ keys, uint64_t n_keys, const uint4
   }
 }
 
+// finish: candidates with summed d <= dist, in key order
+__global__ void k_finish_flags(const uint32_t *__restrict__ d, uint64_t n, int32_t dist, uint8_t *__restrict__ flags) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) flags[e] = (d[e] <= (uint32_t)dist) ? 1 : 0;
+}
+__global__ void k_finish_gather(const uint32_t *__restrict__ idx, const uint64_t *__restrict__ n_sel, const uint64_t *__restrict__ keys,
+                                const uint32_t *__restrict__ d, const uint32_t *__restrict__ u, uint64_t L_total,
+                                uint64_t *__restrict__ keys_o, uint32_t *__restrict__ d_o, uint64_t *__restrict__ rows,
+                                uint64_t *__restrict__ cols, uint64_t *__restrict__ dist, uint64_t *__restrict__ ncomp) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= *n_sel) return;
+  const uint32_t c = idx[e];
+  const uint64_t k = keys[c];
+  keys_o[e] = k;
+  d_o[e] = d[c];
+  rows[e] = k >> 32;
+  cols[e] = k & 0xFFFFFFFFull;
+  dist[e] = d[c];
+  ncomp[e] = L_total - u[c];
+}
+
+// summed candidate vectors (device) -> edge columns on the host
+void site_shard_finish_device(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
+                              uint64_t L_total, const tracs_opts_t &o, HostEdges &out, cudaStream_t st) {
+  tracs_stats_t &S = g_stats;
+  if (n_keys == 0) return;
+  if (n_keys >= (1ull << 32)) throw std::runtime_error("site shard: too many candidates");
+  Timer T(st);
+  T.start();
+  TransLut lut;
+  const bool fuse = lut.setup(o, n, (uint64_t)std::max<int64_t>(o.dist, 0) + 1, st);
+  DevBuf<uint8_t> flags(n_keys);
+  DevBuf<uint32_t> idx(n_keys);
+  DevBuf<uint64_t> n_sel(1);
+  k_finish_flags<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(dev_d, n_keys, o.dist, flags.p);
+  size_t tb = 0;
+  cub::CountingInputIterator<uint32_t> cnt_it(0);
+  cub::DeviceSelect::Flagged(nullptr, tb, cnt_it, flags.p, idx.p, n_sel.p, (int64_t)n_keys, st);
+  DevBuf<uint8_t> tmp(tb);
+  cub::DeviceSelect::Flagged(tmp.p, tb, cnt_it, flags.p, idx.p, n_sel.p, (int64_t)n_keys, st);
+  // columns are sized by the candidate count (an upper bound): no host round trip before the gather
+  DevBuf<uint64_t> keys_o(n_keys), d_rows(n_keys), d_cols(n_keys), d_dist(n_keys), d_nc(n_keys);
+  DevBuf<uint32_t> d_o(n_keys);
+  k_finish_gather<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(idx.p, n_sel.p, dev_keys, dev_d, dev_union, L_total, keys_o.p, d_o.p,
+                                                                   d_rows.p, d_cols.p, d_dist.p, d_nc.p);
+  S.kernel_launches += 4;
+  TRACS_CK(cudaGetLastError());
+  uint64_t E = 0;
+  TRACS_CK(cudaMemcpyAsync(&E, n_sel.p, 8, cudaMemcpyDeviceToHost, st));
+  TRACS_CK(cudaStreamSynchronize(st));
+  S.ms_sort += T.stop();
+  S.n_edges = E;
+  if (E == 0) return;
+  out.rows.resize(E); out.cols.resize(E); out.dist.resize(E); out.ncomp.resize(E);
+  TRACS_CK(cudaMemcpyAsync(out.rows.data(), d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
+  TRACS_CK(cudaMemcpyAsync(out.cols.data(), d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));
+  TRACS_CK(cudaMemcpyAsync(out.dist.data(), d_dist.p, E * 8, cudaMemcpyDeviceToHost, st));
+  TRACS_CK(cudaMemcpyAsync(out.ncomp.data(), d_nc.p, E * 8, cudaMemcpyDeviceToHost, st));
+  S.d2h_bytes += E * 32;
+  DevBuf<double> d_p0, d_eK, d_dt;
+  if (fuse) {
+    T.start();
+    out.has_trans = true;
+    d_p0.alloc(E); d_eK.alloc(E); d_dt.alloc(E);
+    out.p0_log.resize(E); out.eK.resize(E); out.datediff.resize(E);
+    lut.apply(keys_o.p, d_o.p, E, d_p0.p, d_eK.p, d_dt.p, st);
+    S.ms_trans += T.stop();
+    TRACS_CK(cudaMemcpyAsync(out.p0_log.data(), d_p0.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(out.eK.data(), d_eK.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(out.datediff.data(), d_dt.p, E * 8, cudaMemcpyDeviceToHost, st));
+    S.d2h_bytes += E * 24;
+  }
+  T.start();
+  TRACS_CK(cudaStreamSynchronize(st));
+  S.ms_d2h += T.stop();
+}
+
 }  // namespace tracs
 
 using namespace tracs;
@@ -88,7 +165,7 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
     std::unique_ptr<SiteShard> sh(new SiteShard());
     g_stats.n_samples = n;
     g_stats.seq_length = L_slab;
-    ingest_device(dev_slab, n, L_slab, pitch, true, false, sh->ing, st);
+    ingest_device(dev_slab, n, L_slab, pitch, o.packed_input != 0, false, sh->ing, st);
     const Ingested &g = sh->ing;
     const uint64_t i_end = (o.i_end == 0 || o.i_end > n) ? n : o.i_end;
     const int world = std::max(1, (int)o.shard_world), rank = std::max(0, (int)o.shard_rank);

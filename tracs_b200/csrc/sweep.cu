@@ -28,31 +28,6 @@ namespace tracs {
 static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 // ------------------------------------------------------------------------------------------
-// base-mask table: bit0=A bit1=C bit2=G bit3=T ; everything that is not an IUPAC code = 15
-// ------------------------------------------------------------------------------------------
-__host__ __device__ inline uint32_t base_mask(uint32_t c) {
-  c &= 0xFFu;
-  if (c >= 'a' && c <= 'z') c -= 32;
-  switch (c) {
-    case 'A': return 1;
-    case 'C': return 2;
-    case 'G': return 4;
-    case 'T': return 8;
-    case 'M': return 3;
-    case 'R': return 5;
-    case 'W': return 9;
-    case 'S': return 6;
-    case 'Y': return 10;
-    case 'K': return 12;
-    case 'V': return 7;
-    case 'H': return 11;
-    case 'D': return 13;
-    case 'B': return 14;
-    default: return 15;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // K0a: pack
 //   thread <-> one 32-site word (32 ASCII bytes) ; loops over a chunk of samples.
 //   No memory table: PRMT is used as an 8-entry byte table, four lookups per instruction. The index
@@ -138,21 +113,9 @@ __device__ __forceinline__ uint32_t pack_nbit(uint32_t t) {
   return 8u * pos + 4u * (q >> 2) + (q & 3u);
 }
 
-// One sample's 32 sites: lookups, column AND, is-N word, N count and block summary. Lanes past the
-// end of the alignment carry 'N' bytes and validp == 0, so every lane of a warp runs the same code.
+// is-N word of one sample's 32 sites -> N-plane, per-sample N count (shared-memory counter) and block summary.
 // The summary byte is only computed and stored when the warp saw an N at all (the buffer is pre-zeroed).
-__device__ __forceinline__ void pack_one_sample(const uint4 &a, const uint4 &b, uint32_t *np, uint8_t *sp, uint32_t *cnt,
-                                                const uint8_t *slut, uint32_t (&acc)[8], uint32_t validp, uint32_t lane) {
-  uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
-  pack_unit<0, 1>(a.x, a.y, slut, m0, m1);
-  pack_unit<2, 3>(a.z, a.w, slut, m2, m3);
-  pack_unit<0, 1>(b.x, b.y, slut, m4, m5);
-  pack_unit<2, 3>(b.z, b.w, slut, m6, m7);
-  acc[0] &= m0; acc[1] &= m1; acc[2] &= m2; acc[3] &= m3;
-  acc[4] &= m4; acc[5] &= m5; acc[6] &= m6; acc[7] &= m7;
-  // the four flag positions of a half are disjoint: OR them, then interleave the two halves
-  const uint32_t f0 = m0 | m1 | m2 | m3, f1 = m4 | m5 | m6 | m7;
-  const uint32_t isn = bsel(f1, f0 >> 4, 0xF0F0F0F0u) & validp;
+__device__ __forceinline__ void pack_emit_n(uint32_t isn, uint32_t *np, uint8_t *sp, uint32_t *cnt, uint32_t lane) {
   __stcs(np, isn);
   const uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
   if (nz) {
@@ -166,6 +129,23 @@ __device__ __forceinline__ void pack_one_sample(const uint4 &a, const uint4 &b, 
       *sp = (uint8_t)nibbles_all_ones(t2 * 0xFu);
     }
   }
+}
+
+// One sample's 32 sites: lookups, column AND, is-N word, N count and block summary. Lanes past the
+// end of the alignment carry 'N' bytes and validp == 0, so every lane of a warp runs the same code.
+__device__ __forceinline__ void pack_one_sample(const uint4 &a, const uint4 &b, uint32_t *np, uint8_t *sp, uint32_t *cnt,
+                                                const uint8_t *slut, uint32_t (&acc)[8], uint32_t validp, uint32_t lane) {
+  uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
+  pack_unit<0, 1>(a.x, a.y, slut, m0, m1);
+  pack_unit<2, 3>(a.z, a.w, slut, m2, m3);
+  pack_unit<0, 1>(b.x, b.y, slut, m4, m5);
+  pack_unit<2, 3>(b.z, b.w, slut, m6, m7);
+  acc[0] &= m0; acc[1] &= m1; acc[2] &= m2; acc[3] &= m3;
+  acc[4] &= m4; acc[5] &= m5; acc[6] &= m6; acc[7] &= m7;
+  // the four flag positions of a half are disjoint: OR them, then interleave the two halves
+  const uint32_t f0 = m0 | m1 | m2 | m3, f1 = m4 | m5 | m6 | m7;
+  const uint32_t isn = bsel(f1, f0 >> 4, 0xF0F0F0F0u) & validp;
+  pack_emit_n(isn, np, sp, cnt, lane);
 }
 
 // `rows` consecutive samples of one 32-site word. Running pointers (no 64-bit index arithmetic per sample);
@@ -404,6 +384,21 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
   }
 }
 
+}  // namespace tracs
+#include "pack4.inl"
+namespace tracs {
+
+void encode_rows_device(const uint8_t *dev_ascii, uint64_t rows, uint64_t L, uint64_t pitch, uint8_t *dev_nib, uint64_t pitch4,
+                        cudaStream_t st) {
+  if (pitch % 32 != 0 || pitch < round_up(L, 32)) throw std::runtime_error("encode: ASCII pitch must be a multiple of 32 and >= L rounded up to 32");
+  if (pitch4 % 16 != 0 || pitch4 * 2 < std::max<uint64_t>(32, round_up(L, 32))) throw std::runtime_error("encode: packed pitch must be a multiple of 16 bytes and hold L rounded up to 32 sites");
+  const uint64_t total = rows * (pitch4 / 16);
+  if (!total) return;
+  k_encode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dev_ascii, rows, L, pitch, dev_nib, pitch4);
+  g_stats.kernel_launches++;
+  TRACS_CK(cudaGetLastError());
+}
+
 // site s is variable iff its column-AND nibble is 0
 __global__ void k_siteflags(const uint32_t *__restrict__ colmask, uint64_t L, uint8_t *__restrict__ flags) {
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 sites
@@ -418,7 +413,15 @@ __global__ void k_siteflags(const uint32_t *__restrict__ colmask, uint64_t L, ui
   *reinterpret_cast<uint64_t *>(flags + g * 8) = out;
 }
 
+// mask of one site of one row: ASCII byte through the table, or the nibble of the packed format (pack4.inl)
+template <bool PACKED>
+__device__ __forceinline__ uint32_t site_mask(const uint8_t *__restrict__ row, uint64_t site, const uint8_t *lut) {
+  if (PACKED) return ((uint32_t)__ldg(row + (site >> 1)) >> ((site & 1u) * 4u)) & 15u;
+  return lut[__ldg(row + site)];
+}
+
 // K0b: bit-slice the variable sites. One warp per (word, sample-chunk); lane <-> site.
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uint32_t *__restrict__ site_idx, uint64_t V,
          uint4 *__restrict__ planes, uint64_t Npad, uint4 *__restrict__ planesT, uint64_t Wp, uint32_t schunk,
@@ -435,14 +438,14 @@ k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uin
   const uint64_t s0 = (uint64_t)blockIdx.y * schunk, s1 = min(n, s0 + schunk);
   constexpr int GB = 8;  // byte loads in flight per lane
   for (uint64_t sb = s0; sb < s1; sb += GB) {
-    uint8_t ch[GB];
+    uint32_t mk[GB];
 #pragma unroll
-    for (int t = 0; t < GB; ++t) ch[t] = (live && sb + t < s1) ? __ldg(seqs + (sb + t) * pitch + site) : (uint8_t)'N';
+    for (int t = 0; t < GB; ++t) mk[t] = (live && sb + t < s1) ? site_mask<PACKED>(seqs + (sb + t) * pitch, site, lut) : 15u;
 #pragma unroll
     for (int t = 0; t < GB; ++t) {
       const uint64_t s = sb + t;
       if (s >= s1) break;
-      const uint32_t m = live ? lut[ch[t]] : 15u;
+      const uint32_t m = mk[t];
       // two- or three-base codes at a variable site rule out the one-hot GEMM identity (sweep_tc.inl)
       if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) *amb_flag = 1u;
       const uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
@@ -461,6 +464,7 @@ k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uin
 // ---- early-extraction path: byte matrices X[s][e] (mask of listed site e in sample s) -> planes ----------------
 // masks of the listed sites for a sample range (the scattered DRAM pass, used for the first sample chunk and for
 // the sites found variable only later). One warp per 32 listed sites and sample chunk.
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_gather_bytes(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint64_t pitch, const uint32_t *__restrict__ list,
                uint32_t n_list, uint8_t *__restrict__ X, uint64_t XP, uint32_t schunk) {
@@ -475,12 +479,12 @@ k_gather_bytes(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_en
   const uint64_t s0 = s_begin + (uint64_t)blockIdx.y * schunk, s1 = min(s_end, s0 + schunk);
   constexpr int GB = 8;
   for (uint64_t sb = s0; sb < s1; sb += GB) {
-    uint8_t ch[GB];
+    uint32_t mk[GB];
 #pragma unroll
-    for (int t = 0; t < GB; ++t) ch[t] = (live && sb + t < s1) ? __ldg(seqs + (sb + t) * pitch + site) : (uint8_t)'N';
+    for (int t = 0; t < GB; ++t) mk[t] = (live && sb + t < s1) ? site_mask<PACKED>(seqs + (sb + t) * pitch, site, lut) : 15u;
 #pragma unroll
     for (int t = 0; t < GB; ++t)
-      if (live && sb + t < s1) X[(sb + t) * XP + e] = lut[ch[t]];
+      if (live && sb + t < s1) X[(sb + t) * XP + e] = (uint8_t)mk[t];
   }
 }
 
@@ -938,6 +942,9 @@ __global__ void k_pack_edges(const uint64_t *__restrict__ keys, const uint32_t *
   f[e] = p0 ? p0[e] : 0.0;
   f[E + e] = eK ? eK[e] : 0.0;
 }
+struct WidenU32 {
+  __host__ __device__ __forceinline__ uint64_t operator()(const uint32_t &v) const { return (uint64_t)v; }
+};
 __global__ void k_widen(const uint32_t *__restrict__ in, uint64_t E, uint64_t *__restrict__ out) {
   const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < E) out[e] = in[e];
@@ -1045,12 +1052,9 @@ namespace tracs {
 // One launch of the tile sweep over a.n_tiles tiles and a.Wp words: tensor-core kernel when the masks
 // allow its identity (no 2-/3-base codes at variable sites), LOP3/POPC kernel otherwise.
 static void launch_tile_sweep(const SweepArgs &a, bool use_tc, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    TRACS_CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
-    TRACS_CK(cudaFuncSetAttribute(k_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    attr_set = true;
-  }
+  // the opt-in is per device (context): set on every call, it is a cheap driver call
+  TRACS_CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+  TRACS_CK(cudaFuncSetAttribute(k_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -1085,10 +1089,14 @@ struct Ingested {
 };
 
 // ASCII matrix (device) -> N-plane + summaries + variable-site bit-planes (K0a + K0b)
-static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, bool want_n, bool keep_site_idx,
+// `packed`: dev_seqs holds 4-bit masks, two sites per byte (pack4.inl), pitch in bytes
+static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, bool packed, bool keep_site_idx,
                           Ingested &g, cudaStream_t st) {
   tracs_stats_t &S = g_stats;
-  if (pitch % 32 != 0 || pitch < round_up(L, 32)) throw std::runtime_error("device alignment pitch must be a multiple of 32 and >= L rounded up to 32");
+  if (!packed && (pitch % 32 != 0 || pitch < round_up(L, 32)))
+    throw std::runtime_error("device alignment pitch must be a multiple of 32 and >= L rounded up to 32");
+  if (packed && (pitch % 16 != 0 || pitch * 2 < std::max<uint64_t>(32, round_up(L, 32))))
+    throw std::runtime_error("packed alignment pitch must be a multiple of 16 bytes and hold L rounded up to 32 sites");
   Timer T(st);
   g.n = n;
   g.L = L;
@@ -1132,12 +1140,17 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   auto launch_pack = [&](uint64_t sa, uint64_t sb, const uint32_t *elist, uint32_t VE, uint8_t *X, uint64_t XP) {
     if (sb <= sa) return;
     dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((sb - sa + PACK_SCHUNK - 1) / PACK_SCHUNK));
-    if (VE) {
-      static bool attr = false;
-      if (!attr) {
-        attr = true;
-        TRACS_CK(cudaFuncSetAttribute(k_pack_x, cudaFuncAttributePreferredSharedMemoryCarveout, 60));  // 3 x 34 KB per SM
+    if (packed) {
+      if (VE) {
+        TRACS_CK(cudaFuncSetAttribute(k_pack4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+        k_pack4<true><<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p,
+                                                   elist, VE, X, XP);
+      } else {
+        k_pack4<false><<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p,
+                                                    nullptr, 0, nullptr, 0);
       }
+    } else if (VE) {
+      TRACS_CK(cudaFuncSetAttribute(k_pack_x, cudaFuncAttributePreferredSharedMemoryCarveout, 60));  // 3 x 34 KB per SM (per device)
       k_pack_x<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p, elist,
                                             VE, X, XP);
     } else {
@@ -1201,7 +1214,8 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
     TRACS_CK(cudaMemsetAsync(amb.p, 0, 4, st));
     if (!early) {
       dim3 grid((unsigned)((W + 7) / 8), (unsigned)((n + schunk - 1) / schunk));
-      k_gather<<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, g.planes.p, Npad, g.planesT.p, Wp, schunk, amb.p);
+      if (packed) k_gather<true><<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, g.planes.p, Npad, g.planesT.p, Wp, schunk, amb.p);
+      else k_gather<false><<<grid, 256, 0, st>>>(dev_seqs, n, pitch, site_idx.p, V, g.planes.p, Npad, g.planesT.p, Wp, schunk, amb.p);
       S.kernel_launches++;
     } else {
       // listed sites of the first chunk, late sites of every sample: the scattered pass; then bit-slice
@@ -1210,13 +1224,16 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
       DevBuf<uint8_t> X2;
       const uint64_t X2P = round_up(std::max<uint64_t>(1, VL), 32);
       k_site_sources<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(site_idx.p, (uint32_t)V, elist.p, (uint32_t)VE, src.p, late.p);
-      k_gather_bytes<<<dim3((unsigned)((VE + 255) / 256), (unsigned)((n_first + schunk - 1) / schunk)), 256, 0, st>>>(
-          dev_seqs, 0, n_first, pitch, elist.p, (uint32_t)VE, X.p, XP, schunk);
+      auto gather_bytes = [&](uint64_t sa, uint64_t sb, const uint32_t *list, uint64_t n_list, uint8_t *dst, uint64_t dpitch) {
+        const dim3 gg((unsigned)((n_list + 255) / 256), (unsigned)((sb - sa + schunk - 1) / schunk));
+        if (packed) k_gather_bytes<true><<<gg, 256, 0, st>>>(dev_seqs, sa, sb, pitch, list, (uint32_t)n_list, dst, dpitch, schunk);
+        else k_gather_bytes<false><<<gg, 256, 0, st>>>(dev_seqs, sa, sb, pitch, list, (uint32_t)n_list, dst, dpitch, schunk);
+      };
+      gather_bytes(0, n_first, elist.p, VE, X.p, XP);
       S.kernel_launches += 2;
       if (VL) {
         X2.alloc(n * X2P);
-        k_gather_bytes<<<dim3((unsigned)((VL + 255) / 256), (unsigned)((n + schunk - 1) / schunk)), 256, 0, st>>>(
-            dev_seqs, 0, n, pitch, late.p, (uint32_t)VL, X2.p, X2P, schunk);
+        gather_bytes(0, n, late.p, VL, X2.p, X2P);
         S.kernel_launches++;
       }
       dim3 grid((unsigned)((W + 15) / 16), (unsigned)((n + schunk - 1) / schunk));
@@ -1232,6 +1249,58 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   S.ms_compact += T.stop();
   if (!keep_site_idx) site_idx.release();
 }
+
+// Fused transmission likelihood (K3) for a sorted device edge list: dense table over (d, day difference).
+struct TransLut {
+  bool on = false;
+  uint32_t DD = 0;
+  uint64_t lut_size = 0;
+  double lamb = 0, beta = 0, thr = 0;
+  DevBuf<int32_t> d_days;
+  DevBuf<double> d_lg, p0_lut, eK_lut;
+  DevBuf<uint8_t> used, sel_tmp;
+  DevBuf<uint32_t> key_idx;
+  DevBuf<uint64_t> n_keys;
+  size_t sel_tmp_bytes = 0;
+  // d_top: distances are < d_top. Returns false (table too large / not requested): the caller falls back to the
+  // unique-key path on the host side (trans_dist_device).
+  bool setup(const tracs_opts_t &o, uint64_t n, uint64_t d_top, cudaStream_t st) {
+    if (!(o.want_trans && o.days) || o.dist < 0) return false;
+    int32_t dmin = o.days[0], dmaxday = o.days[0];
+    for (uint64_t s = 0; s < n; ++s) {
+      dmin = std::min(dmin, o.days[s]);
+      dmaxday = std::max(dmaxday, o.days[s]);
+    }
+    const uint64_t dd_span = (uint64_t)((int64_t)dmaxday - (int64_t)dmin) + 1;
+    if (dd_span * d_top > (1ull << 24)) return false;
+    on = true;
+    DD = (uint32_t)dd_span;
+    lut_size = dd_span * d_top;
+    lamb = o.lamb; beta = o.beta; thr = o.threshold_Ek;
+    d_days.alloc(n);
+    TRACS_CK(cudaMemcpyAsync(d_days.p, o.days, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const size_t nlg = (size_t)d_top + 10000 + 8;
+    const auto lg_keep = lgamma_table(nlg);
+    d_lg.alloc(nlg);
+    TRACS_CK(cudaMemcpyAsync(d_lg.p, lg_keep->data(), nlg * 8, cudaMemcpyHostToDevice, st));
+    p0_lut.alloc(lut_size); eK_lut.alloc(lut_size); used.alloc(lut_size); key_idx.alloc(lut_size); n_keys.alloc(1);
+    cub::CountingInputIterator<uint32_t> cnt_it(0);
+    cub::DeviceSelect::Flagged(nullptr, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
+    sel_tmp.alloc(sel_tmp_bytes);
+    return true;
+  }
+  // keys (i << 32 | j) and distances of E edges -> log p0, E[K], date difference (years), all device arrays
+  void apply(const uint64_t *keys, const uint32_t *dvals, uint64_t E, double *p0, double *eK, double *dt, cudaStream_t st) {
+    TRACS_CK(cudaMemsetAsync(used.p, 0, lut_size, st));
+    k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys, dvals, E, d_days.p, DD, used.p);
+    cub::CountingInputIterator<uint32_t> cnt_it(0);
+    cub::DeviceSelect::Flagged(sel_tmp.p, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
+    k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, st>>>(key_idx.p, n_keys.p, DD, d_lg.p, lamb, beta, thr, p0_lut.p, eK_lut.p);
+    k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys, dvals, E, d_days.p, DD, p0_lut.p, eK_lut.p, p0, eK, dt);
+    g_stats.kernel_launches += 5;
+    TRACS_CK(cudaGetLastError());
+  }
+};
 
 // which row-blocks a shard sweeps, and how many pairs each holds
 struct TilePlan {
@@ -1275,7 +1344,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   Ttot.start();
   const bool want_n = o.want_ncomp != 0;
   Ingested ing;
-  ingest_device(dev_seqs, n, L, pitch, want_n, o.filter != 0, ing, st);
+  ingest_device(dev_seqs, n, L, pitch, o.packed_input != 0, o.filter != 0, ing, st);
   const uint64_t npitch = ing.npitch, spitch = ing.spitch, V = ing.V, W = ing.W;
   const uint32_t Wp = ing.Wp, Npad = ing.Npad;
   DevBuf<uint32_t> &nplane = ing.nplane, &ncount = ing.ncount, &site_idx = ing.site_idx;
@@ -1329,41 +1398,9 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   DevBuf<uint8_t> sort_tmp(sort_tmp_bytes);
 
   // ---- fused transmission likelihood set-up (device table over (d, day difference)) ----------
-  bool fuse_trans = false;
-  uint32_t DD = 0;
-  uint64_t lut_size = 0;
-  DevBuf<int32_t> d_days;
-  DevBuf<double> d_lg, p0_lut, eK_lut;
-  DevBuf<uint8_t> used;
-  DevBuf<uint32_t> key_idx;
-  DevBuf<uint64_t> n_keys;
-  DevBuf<uint8_t> sel_tmp;
-  size_t sel_tmp_bytes = 0;
-  if (o.want_trans && o.days) {
-    int32_t dmin = o.days[0], dmaxday = o.days[0];
-    for (uint64_t s = 0; s < n; ++s) {
-      dmin = std::min(dmin, o.days[s]);
-      dmaxday = std::max(dmaxday, o.days[s]);
-    }
-    const uint64_t dd_span = (uint64_t)((int64_t)dmaxday - (int64_t)dmin) + 1;
-    const uint64_t d_top = (uint64_t)std::min<int64_t>(std::max<int64_t>(o.dist, 0), (int64_t)Wp * 32) + 1;
-    if (o.dist >= 0 && dd_span * d_top <= (1ull << 24)) {
-      fuse_trans = true;
-      DD = (uint32_t)dd_span;
-      lut_size = dd_span * d_top;
-      d_days.alloc(n);
-      TRACS_CK(cudaMemcpyAsync(d_days.p, o.days, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      const size_t nlg = (size_t)d_top + 10000 + 8;
-      const std::vector<double> &lg = lgamma_table(nlg);
-      d_lg.alloc(nlg);
-      TRACS_CK(cudaMemcpyAsync(d_lg.p, lg.data(), nlg * 8, cudaMemcpyHostToDevice, st));
-      p0_lut.alloc(lut_size); eK_lut.alloc(lut_size); used.alloc(lut_size); key_idx.alloc(lut_size); n_keys.alloc(1);
-      cub::CountingInputIterator<uint32_t> cnt_it(0);
-      cub::DeviceSelect::Flagged(nullptr, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
-      sel_tmp.alloc(sel_tmp_bytes);
-      out.has_trans = true;
-    }
-  }
+  TransLut lut;
+  const bool fuse_trans = lut.setup(o, n, (uint64_t)std::min<int64_t>(std::max<int64_t>(o.dist, 0), (int64_t)Wp * 32) + 1, st);
+  if (fuse_trans) out.has_trans = true;
 
   for (size_t b = 0; b < bands.size(); ++b) {
     std::vector<uint32_t> rbs(my_rb.begin() + bands[b].first, my_rb.begin() + bands[b].second);
@@ -1456,9 +1493,11 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       DevBuf<uint8_t> stmp;
       size_t sb = 0;
       TRACS_CK(cudaMemsetAsync(offs.p, 0, sizeof(uint64_t), st));
-      cub::DeviceScan::InclusiveSum(nullptr, sb, dv2.p, offs.p + 1, (int64_t)E, st);
+      // the scan accumulates in the INPUT type: widen on the fly so offsets above 2^32 do not wrap
+      cub::TransformInputIterator<uint64_t, WidenU32, const uint32_t *> d_in64(dv2.p, WidenU32());
+      cub::DeviceScan::InclusiveSum(nullptr, sb, d_in64, offs.p + 1, (int64_t)E, st);
       stmp.alloc(sb);
-      cub::DeviceScan::InclusiveSum(stmp.p, sb, dv2.p, offs.p + 1, (int64_t)E, st);
+      cub::DeviceScan::InclusiveSum(stmp.p, sb, d_in64, offs.p + 1, (int64_t)E, st);
       uint64_t total = 0;
       TRACS_CK(cudaMemcpyAsync(&total, offs.p + E, 8, cudaMemcpyDeviceToHost, st));
       TRACS_CK(cudaStreamSynchronize(st));
@@ -1486,7 +1525,8 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       }
       DevBuf<uint32_t> pos(std::max<uint64_t>(1, total));
       const size_t nlg = 10000 + 16;
-      const std::vector<double> &lgh = lgamma_table(nlg);
+      const auto lgh_keep = lgamma_table(nlg);
+      const std::vector<double> &lgh = *lgh_keep;
       DevBuf<double> lg_f(nlg);
       TRACS_CK(cudaMemcpyAsync(lg_f.p, lgh.data(), nlg * 8, cudaMemcpyHostToDevice, st));
       for (size_t c = 0; c + 1 < cuts.size(); ++c) {
@@ -1534,18 +1574,8 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     if (fuse_trans) {
       T.start();
       d_p0.alloc(E); d_eK.alloc(E); d_dt.alloc(E);
-      TRACS_CK(cudaMemsetAsync(used.p, 0, lut_size, st));
       // with the filter on, the likelihood is fed the filtered distance (tracs/distance.py:182-192)
-      const uint32_t *dtrans = o.filter ? d_filt32.p : dv2.p;
-      k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dtrans, E, d_days.p, DD, used.p);
-      cub::CountingInputIterator<uint32_t> cnt_it(0);
-      cub::DeviceSelect::Flagged(sel_tmp.p, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
-      k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, st>>>(key_idx.p, n_keys.p, DD, d_lg.p, o.lamb, o.beta, o.threshold_Ek,
-                                                                    p0_lut.p, eK_lut.p);
-      k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dtrans, E, d_days.p, DD, p0_lut.p, eK_lut.p, d_p0.p,
-                                                                 d_eK.p, d_dt.p);
-      S.kernel_launches += 5;
-      TRACS_CK(cudaGetLastError());
+      lut.apply(keys2.p, o.filter ? d_filt32.p : dv2.p, E, d_p0.p, d_eK.p, d_dt.p, st);
       S.ms_trans += T.stop();
       TRACS_CK(cudaEventRecord(ev_trans, st));
       TRACS_CK(cudaStreamWaitEvent(cs, ev_trans, 0));
@@ -1583,7 +1613,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       TRACS_CK(cudaMalloc(&dp, std::max<size_t>(32, 32 * E)));
       out.dev_packed = dp;
       out.dev_packed_bytes = 32 * E;
-      k_pack_edges<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, o.filter ? d_filt32.p : dv2.p, want_n ? d_nc.p : nullptr,
+      k_pack_edges<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys2.p, dv2.p, want_n ? d_nc.p : nullptr,
                                                                fuse_trans ? d_p0.p : nullptr, fuse_trans ? d_eK.p : nullptr, E,
                                                                (uint8_t *)dp);
       S.kernel_launches++;
@@ -1602,3 +1632,4 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
 }  // namespace tracs
 
 #include "shard.inl"
+#include "tc_peak.inl"

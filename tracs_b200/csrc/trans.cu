@@ -16,6 +16,8 @@
 // (SURVEY F6). That closed form is returned here.
 #include <math.h>
 
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <unordered_map>
 #include <vector>
@@ -35,14 +37,19 @@ __global__ void k_trans_keys(const int32_t *__restrict__ keyN, const double *__r
 
 // lg[x] = lgamma(x) by the host libm, like the reference's table (transcluster.hpp:253-258) but long
 // enough that k < 10000 never reads past it. Cached across calls.
-const std::vector<double> &lgamma_table(size_t n) {
-  static std::vector<double> lg;
-  if (lg.size() < n) {
-    size_t old = lg.size();
-    lg.resize(n);
-    for (size_t i = old; i < n; ++i) lg[i] = ::lgamma((double)i);
+// Returns a snapshot (shared, immutable): concurrent callers on other threads may grow the table meanwhile.
+std::shared_ptr<const std::vector<double>> lgamma_table(size_t n) {
+  static std::mutex mu;
+  static std::shared_ptr<const std::vector<double>> cur;
+  std::lock_guard<std::mutex> g(mu);
+  if (!cur || cur->size() < n) {
+    auto nx = std::make_shared<std::vector<double>>(cur ? *cur : std::vector<double>());
+    const size_t old = nx->size();
+    nx->resize(n);
+    for (size_t i = old; i < n; ++i) (*nx)[i] = ::lgamma((double)i);
+    cur = nx;
   }
-  return lg;
+  return cur;
 }
 
 namespace {
@@ -81,7 +88,8 @@ void trans_dist_device(const int32_t *snp, const double *dt, size_t n, double la
   const uint32_t nk = (uint32_t)kN.size();
   // lg[x] = lgamma(x), host libm like the reference (transcluster.hpp:253-258), long enough for k < 10000
   const size_t nlg = (size_t)maxN + 10000 + 8;
-  const std::vector<double> &lg = lgamma_table(nlg);
+  const auto lg_keep = lgamma_table(nlg);
+  const std::vector<double> &lg = *lg_keep;
   DevBuf<double> d_lg(nlg), d_kD(nk), d_p0(nk), d_eK(nk);
   DevBuf<int32_t> d_kN(nk);
   Timer T(st);

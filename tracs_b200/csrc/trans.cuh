@@ -40,7 +40,7 @@ __device__ __forceinline__ void trans_eval(int64_t N, double delta, const double
   const double ub = exp(ln_b + delta * lamb + log((double)(N + 1)) - (ln_l + pois));
   double lprob = -INFINITY, elprob = -INFINITY, diff = thr + 1.0;
   int64_t k = 1;
-  while (!(diff <= thr) && k < 10000) {
+  while (diff > thr && k < 10000) {  // a NaN bound ends the loop after one term, like the reference's `diff > threshold_Ek`
     const int64_t M = N + k;
     G = lae((double)M * lx - lg[M + 1], G);
     const double lhs = common + (double)k * ln_b + lg[M + 1] - lg[k + 1];

@@ -9,9 +9,15 @@ compact 32 B/edge layout (u32 row, col, d, compared sites; f64 log p0, E[K]) thr
 page-locked staging buffer."""
 import numpy as np
 
-COLUMNS = ("rows", "cols", "dist", "ncomp", "p0_log", "eK")
-_DTYPES = (np.uint32, np.uint32, np.uint32, np.uint32, np.float64, np.float64)
-_BYTES_PER_EDGE = 4 * 4 + 2 * 8
+# host-staged path: every column of the edge table (44 B/edge); GPU-to-GPU path: the library's packed block
+# (tracs_edges_t.dev_packed, 32 B/edge: rows, cols, RAW dist, ncomp, p0_log, eK -- no filt / datediff, so it is
+# only taken when the recombination filter is off; datediff is then recomputed by the caller if needed)
+COLUMNS = ("rows", "cols", "dist", "ncomp", "filt", "p0_log", "eK", "datediff")
+_DTYPES = (np.uint32, np.uint32, np.uint32, np.uint32, np.uint32, np.float64, np.float64, np.float64)
+_BYTES_PER_EDGE = 5 * 4 + 3 * 8
+DEV_COLUMNS = ("rows", "cols", "dist", "ncomp", "p0_log", "eK")
+_DEV_DTYPES = (np.uint32, np.uint32, np.uint32, np.uint32, np.float64, np.float64)
+_DEV_BYTES_PER_EDGE = 4 * 4 + 2 * 8
 TILE = 128
 
 
@@ -21,10 +27,10 @@ def shard_owner(row_block, world):
     return (world - 1 - pos) if (rnd & 1) else pos
 
 
-def _sections(buf, mx):
-    """Typed views of the six column sections inside a flat uint8 numpy buffer of 32*mx bytes."""
+def _sections(buf, mx, dtypes=_DTYPES):
+    """Typed views of the column sections inside a flat uint8 numpy buffer of bytes_per_edge*mx bytes."""
     out, off = [], 0
-    for dt in _DTYPES:
+    for dt in dtypes:
         nb = np.dtype(dt).itemsize * mx
         out.append(buf[off:off + nb].view(dt))
         off += nb
@@ -41,7 +47,7 @@ def merge_by_rowblock(parts, world):
     n_rb = top // TILE + 1
     bounds = [np.searchsorted(p["rows"], np.arange(n_rb + 1, dtype=np.uint64) * TILE) for p in parts]
     out = {}
-    for c in COLUMNS:
+    for c in parts[0].keys():
         out[c] = np.concatenate([parts[shard_owner(rb, world)][c][bounds[shard_owner(rb, world)][rb]:bounds[shard_owner(rb, world)][rb + 1]]
                                  for rb in range(n_rb)]) if n_rb else parts[0][c][:0]
     return out
@@ -79,9 +85,12 @@ class EdgeGather:
         dist.all_gather(cnts, cnt)
         cnts = [int(c.item()) for c in cnts]
         dp = res.get("dev_packed") if hasattr(res, "get") else None
-        if dp is not None and self.device.type == "cuda":
+        filt = res.get("filt") if hasattr(res, "get") else None
+        has_filt = filt is not None and len(filt) and bool(np.any(np.asarray(filt)))
+        if dp is not None and self.device.type == "cuda" and not has_filt:
             return self._gather_device(res, dp, cnts, merge)
         mx = max(cnts + [1])
+        mx += mx & 1   # five u32 sections in front of the f64 ones: keep those 8-byte aligned
         nbytes = _BYTES_PER_EDGE * mx
         self.send = self._host(nbytes, self.send)
         secs = _sections(self.send.numpy()[:nbytes], mx)
@@ -121,15 +130,15 @@ def _gather_device_impl(self, res, dp, cnts, merge):
         if nbytes:
             dist.send(mine, dst=0)
         return None
-    bufs = [mine] + [torch.empty(_BYTES_PER_EDGE * cnts[r], dtype=torch.uint8, device=self.device) for r in range(1, self.world)]
+    bufs = [mine] + [torch.empty(_DEV_BYTES_PER_EDGE * cnts[r], dtype=torch.uint8, device=self.device) for r in range(1, self.world)]
     reqs = [dist.irecv(bufs[r], src=r) for r in range(1, self.world) if cnts[r]]
     for q in reqs:
         q.wait()
-    total = _BYTES_PER_EDGE * sum(cnts)
+    total = _DEV_BYTES_PER_EDGE * sum(cnts)
     self.recv = self._host(total, self.recv)
     off, spans = 0, []
     for r in range(self.world):
-        nb = _BYTES_PER_EDGE * cnts[r]
+        nb = _DEV_BYTES_PER_EDGE * cnts[r]
         if nb:
             self.recv[off:off + nb].copy_(bufs[r], non_blocking=True)
         spans.append((off, nb))
@@ -138,8 +147,8 @@ def _gather_device_impl(self, res, dp, cnts, merge):
     host = self.recv.numpy()
     parts = []
     for r, (o, nb) in enumerate(spans):
-        secs = _sections(host[o:o + nb], cnts[r])
-        parts.append({c: s for c, s in zip(COLUMNS, secs)})
+        secs = _sections(host[o:o + nb], cnts[r], _DEV_DTYPES)
+        parts.append({c: s for c, s in zip(DEV_COLUMNS, secs)})
     return merge_by_rowblock(parts, self.world) if merge else parts
 
 
