@@ -436,6 +436,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the forced full-length sweeps reported under roofline_kernels")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--profile-phases", action="store_true", help="N>1: one extra untimed step with per-phase host timers (stages_ms.phases_ms)")
     args = ap.parse_args()
     if args.n or args.L:
         for c in CONFIGS.values():
@@ -511,6 +512,7 @@ def main():
     def timed(fn, steps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stats, res = [], None
+        res, _ = fn()   # untimed: this loop's own result slot (the previous result stays alive while a call runs)
         sync()
         t0 = time.perf_counter()
         ev0.record()
@@ -529,7 +531,9 @@ def main():
     if rank == 0:
         clocks.start()
     for _ in range(args.warmup):
-        held = step()   # held like in the timed loop, so the result-buffer cache reaches its steady state
+        res = step()   # one result held while the next call runs, like in the timed loop: the page-locked result-buffer cache
+        #                reaches its steady state (two sets of columns) before the clock starts
+    del res
     clocks.mark()
     ms_per_step, wall_per_step, stats, res = timed(step, args.steps)
     clk = clocks.stop() if rank == 0 else None
@@ -565,6 +569,11 @@ def main():
         }
         if strong:
             line["collectives"] = ["ncclAllGather (candidate counts + keys)", "ncclAllReduce (partial d, |N u N|)"]
+    if strong and args.profile_phases:
+        _, stp = sites.sweep(torch, dist_mod, device, rank, world, inp.buf.data_ptr(), n, inp.Ls, inp.pitch, L, w["dist"], days=inp.days,
+                             lamb=w["lamb"], beta=w["beta"], threshold_Ek=w["threshold_Ek"], packed=inp.packed, profile=True)
+        if rank == 0:
+            line["stages_ms"]["phases_ms_rank0"] = stp.get("phases_ms")
         # ---- the same tile kernels forced over the full length (what an unthresholded / dense run executes) ----------
         if world == 1 and not args.no_extra:
             for nm, variant in (("k_sweep_full_length", True), ("k_sweep_tc_full_length", "tc")):

@@ -90,7 +90,7 @@ def test_packed_early_extraction_matches_oracle(oracle_mod, monkeypatch, n, L, p
     monkeypatch.setenv("TRACS_INGEST", "early")
     res = tracs_b200.pairsnp_packed_host(nib, L, dist=dist)
     st = tracs_b200.last_stats()
-    assert st["n_early_sites"] > 0
+    assert st["n_early_sites"] > 0 or p_var > 1.0 / 16   # more than L/16 early sites: the ingest keeps the two-pass path
     _cmp(res, orc)
     monkeypatch.setenv("TRACS_INGEST", "split")
     _cmp(tracs_b200.pairsnp_packed_host(nib, L, dist=dist), orc)

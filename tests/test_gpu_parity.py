@@ -88,11 +88,11 @@ def test_prefilter_refine_and_fallback(oracle_mod, n_clusters, dist, expect):
     _cmp(res, oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4))
     assert st["n_words"] >= 256
     if expect == "refine":
-        # dist 0 / 20: the 16-word window (512 variable sites) is enough
-        assert st["ms_refine"] > 0 and st["swept_wordpairs"] == st["n_pairs"] * 16
+        # dist 0 / 20: the first window (8 words = 256 variable sites) is enough
+        assert st["ms_refine"] > 0 and st["swept_wordpairs"] == st["n_pairs"] * 8
     elif expect == "fallback":
-        # too many pairs survive the 16-word and then the 64-word window: both attempts, then the full-length sweep
-        assert st["ms_refine"] == 0 and st["n_candidates"] > 0 and st["swept_wordpairs"] > st["n_pairs"] * (16 + 64)
+        # too many pairs survive the 8-, 16- and 64-word windows: three attempts, then the full-length sweep
+        assert st["ms_refine"] == 0 and st["n_candidates"] > 0 and st["swept_wordpairs"] > st["n_pairs"] * (8 + 16 + 64)
     full = tracs_b200.pairsnp_matrix(s, dist=dist, full_sweep=True)
     st2 = tracs_b200.last_stats()
     assert st2["n_candidates"] == 0 and st2["ms_refine"] == 0
@@ -267,7 +267,7 @@ def test_filter_golden_and_fused_trans(oracle_mod):
 
 def test_device_packed_columns_match_host():
     import torch
-    from tracs_b200.multi import _DevBytes, _sections, COLUMNS
+    from tracs_b200.multi import _DevBytes, _sections, DEV_COLUMNS, _DEV_DTYPES
     s = synth.generate(300, 4000, p_var=0.05, n_clusters=4, mu=3, p_N=0.01, seed=61)
     days = np.random.default_rng(1).integers(0, 50, size=300).astype(np.int32)
     res = tracs_b200.pairsnp_matrix(s, dist=60, days=days, copy=False, keep_on_device=True)
@@ -275,7 +275,7 @@ def test_device_packed_columns_match_host():
     E = len(res["rows"])
     assert nbytes == 32 * E and E > 0
     host = torch.as_tensor(_DevBytes(ptr, nbytes), device="cuda").cpu().numpy()
-    secs = dict(zip(COLUMNS, _sections(host, E)))
+    secs = dict(zip(DEV_COLUMNS, _sections(host, E, _DEV_DTYPES)))
     for c in ("rows", "cols", "dist", "ncomp"):
         assert secs[c].astype(np.uint64).tolist() == res[c].tolist()
     assert np.array_equal(secs["p0_log"], res["p0_log"]) and np.array_equal(secs["eK"], res["eK"])

@@ -52,8 +52,10 @@ void *dev_cache_alloc(size_t bytes) {
       return p;
     }
   }
+  static const bool debug = getenv("TRACS_DEBUG_ALLOC") != nullptr;
   void *p = nullptr;
   cudaError_t e = cudaMalloc(&p, want);
+  if (debug) fprintf(stderr, "[tracs alloc] cudaMalloc %zu MB -> %s\n", want >> 20, cudaGetErrorName(e));
   if (e == cudaErrorMemoryAllocation) {  // make room: drop every idle block of this device and retry once
     cudaGetLastError();
     std::vector<void *> drop;

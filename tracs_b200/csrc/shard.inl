@@ -178,39 +178,53 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
     DevBuf<unsigned long long> counter(1);
     TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
     const bool tc_ok = o.sweep_variant != 1 && !g.partial_ambiguity;
-    const uint32_t words = std::min<uint32_t>(prefilter_words(o.dist), g.Wp);  // Wp is a multiple of KC; any prefix gives a lower bound
     DevBuf<uint32_t> d_rb(std::max<size_t>(1, plan.my_rb.size())), d_prefix(plan.my_rb.size() + 1);
-    size_t k0 = 0;
-    T.start();
-    while (k0 < plan.my_rb.size()) {
-      std::vector<uint32_t> rbs, prefix{0};
-      uint64_t tiles = 0, pairs = 0;
-      size_t k1 = k0;
-      while (k1 < plan.my_rb.size() && tiles < (1ull << 30)) {
-        tiles += plan.n_cb - std::max(plan.my_rb[k1], plan.cb_min);
-        pairs += plan.rb_pairs[k1];
-        rbs.push_back(plan.my_rb[k1]);
-        prefix.push_back((uint32_t)tiles);
-        ++k1;
-      }
-      TRACS_CK(cudaMemcpyAsync(d_rb.p, rbs.data(), rbs.size() * 4, cudaMemcpyHostToDevice, st));
-      TRACS_CK(cudaMemcpyAsync(d_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, st));
-      SweepArgs a;
-      a.planes = g.planes.p; a.Wp = words; a.Npad = g.Npad; a.n = (uint32_t)n; a.i_end = (uint32_t)i_end;
-      a.j_start = (uint32_t)o.j_start; a.dist = o.dist; a.rb_list = d_rb.p; a.tile_prefix = d_prefix.p;
-      a.n_rb = (uint32_t)rbs.size(); a.n_tiles = (uint32_t)tiles; a.cb_min = plan.cb_min; a.counter = counter.p;
-      a.keys = keys.p; a.dvals = dv.p; a.cap = CAND_CAP; a.one = 1;
-      launch_tile_sweep(a, tc_ok, st);
-      TRACS_CK(cudaStreamSynchronize(st));  // rbs/prefix are reused by the next cut
-      g_stats.n_tiles += tiles;
-      g_stats.n_pairs += pairs;
-      g_stats.swept_wordpairs += pairs * words;
-      k0 = k1;
-    }
-    g_stats.ms_sweep += T.stop();
+    uint64_t my_pairs = 0;
+    for (uint64_t p : plan.rb_pairs) my_pairs += p;
+    g_stats.n_pairs = my_pairs;
     unsigned long long nc = 0;
-    TRACS_CK(cudaMemcpyAsync(&nc, counter.p, sizeof nc, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaStreamSynchronize(st));
+    // windows of 8, 16, 64 local words (any prefix of the slab's words gives a lower bound of d), widened while more
+    // than 4 % of this rank's pairs survive; Wp is a multiple of KC. Kernel choice as in sweep_device.
+    const uint32_t first = o.dist < 32 ? 8u : prefilter_words(o.dist);
+    for (uint32_t pw = first;; pw = pw < 16 ? 16 : PREFILTER_WORDS) {
+      const uint32_t words = std::min<uint32_t>(pw, g.Wp);
+      TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+      size_t k0 = 0;
+      T.start();
+      while (k0 < plan.my_rb.size()) {
+        std::vector<uint32_t> rbs, prefix{0};
+        uint64_t tiles = 0;
+        size_t k1 = k0;
+        while (k1 < plan.my_rb.size() && tiles < (1ull << 30)) {
+          tiles += plan.n_cb - std::max(plan.my_rb[k1], plan.cb_min);
+          rbs.push_back(plan.my_rb[k1]);
+          prefix.push_back((uint32_t)tiles);
+          ++k1;
+        }
+        TRACS_CK(cudaMemcpyAsync(d_rb.p, rbs.data(), rbs.size() * 4, cudaMemcpyHostToDevice, st));
+        TRACS_CK(cudaMemcpyAsync(d_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, st));
+        SweepArgs a;
+        a.planes = g.planes.p; a.Wp = words; a.Npad = g.Npad; a.n = (uint32_t)n; a.i_end = (uint32_t)i_end;
+        a.j_start = (uint32_t)o.j_start; a.dist = o.dist; a.rb_list = d_rb.p; a.tile_prefix = d_prefix.p;
+        a.n_rb = (uint32_t)rbs.size(); a.n_tiles = (uint32_t)tiles; a.cb_min = plan.cb_min; a.counter = counter.p;
+        a.keys = keys.p; a.dvals = dv.p; a.cap = CAND_CAP; a.one = 1;
+        DevBuf<uint2> d_table(std::max<uint64_t>(1, tiles));
+        if (tiles) {
+          k_tile_table<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(d_rb.p, d_prefix.p, a.n_rb, plan.cb_min, (uint32_t)tiles, d_table.p);
+          g_stats.kernel_launches++;
+        }
+        a.tile_table = d_table.p;
+        launch_tile_sweep(a, tc_ok && words > 16, st);
+        TRACS_CK(cudaStreamSynchronize(st));  // rbs/prefix are reused by the next cut
+        g_stats.n_tiles += tiles;
+        k0 = k1;
+      }
+      g_stats.ms_sweep += T.stop();
+      g_stats.swept_wordpairs += my_pairs * words;
+      TRACS_CK(cudaMemcpyAsync(&nc, counter.p, sizeof nc, cudaMemcpyDeviceToHost, st));
+      TRACS_CK(cudaStreamSynchronize(st));
+      if ((nc <= CAND_CAP && nc * 25 <= my_pairs) || words >= std::min<uint32_t>(PREFILTER_WORDS, g.Wp)) break;
+    }
     if (nc > CAND_CAP)
       throw std::runtime_error("site-sharded sweep: the prefilter left too many candidate pairs; use the single-GPU / tile-sharded path");
     g_stats.n_candidates = nc;

@@ -609,6 +609,7 @@ struct SweepArgs {
   uint32_t n_rb;
   uint32_t n_tiles;
   uint32_t cb_min;  // first col-block allowed by j_start
+  const uint2 *tile_table;  // [n_tiles] (row-block, col-block) of every tile of the launch (k_tile_table)
   unsigned long long *counter;
   uint64_t *keys;
   uint32_t *dvals;
@@ -645,6 +646,32 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
+// tile -> (row-block, col-block), once per launch list: the tile kernels then need one 8-byte load per tile instead of
+// a binary search over the prefix array (ten dependent L2 round trips: 40 % of an 8-word prefilter tile)
+__global__ void k_tile_table(const uint32_t *__restrict__ rb_list, const uint32_t *__restrict__ tile_prefix, uint32_t n_rb, uint32_t cb_min,
+                             uint32_t n_tiles, uint2 *__restrict__ table) {
+  const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= n_tiles) return;
+  uint32_t lo = 0, hi = n_rb;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const uint32_t rb = rb_list[lo];
+  table[tile] = make_uint2(rb, max(rb, cb_min) + (tile - tile_prefix[lo]));
+}
+
+// acc[b >> 3][b & 7] of a register-resident 8 x 8 array (fully unrolled select: no local-memory spill)
+__device__ __forceinline__ uint32_t acc_at(const uint32_t (&acc)[8][8], int b) {
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (b == i * 8 + j) v = acc[i][j];
+  return v;
+}
+
 constexpr int SWEEP_THREADS = 256;
 constexpr int STAGE_U4 = KC * TILE;  // uint4 per stage per side
 constexpr uint32_t PREFILTER_WORDS = 64;  // widest prefilter window: 2048 variable sites
@@ -661,6 +688,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
   uint4 *srow = reinterpret_cast<uint4 *>(smem_raw);       // [STAGES][KC][TILE]
   uint4 *scol = srow + (size_t)STAGES * STAGE_U4;          // [STAGES][KC][TILE]
   __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ uint2 s_tile[4];  // coordinates of the tiles whose panels are in flight (written by the issuing thread)
 
   const uint32_t tid = threadIdx.x;
   const uint32_t tx = tid & 15, ty = tid >> 4;
@@ -672,35 +700,45 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
 
   const uint32_t nk = a.Wp / KC;
   const uint32_t one = a.one;
-  uint32_t it = 0;  // running chunk counter (stage = it % STAGES, parity = (it / STAGES) & 1)
-
-  for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    // tile -> (row-block, col-block)
-    uint32_t lo = 0, hi = a.n_rb;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (a.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+  // The panels of ALL tiles of this CTA form one stream of chunks g = tile_iter * nk + c (stage = g % STAGES, parity =
+  // (g / STAGES) & 1): chunk g + STAGES is requested as soon as chunk g has been consumed, whichever tile it belongs to,
+  // so the first panels of the next tile arrive during the epilogue of this one (short prefilter windows have 1-2
+  // chunks per tile and would otherwise expose the full load latency on every tile).
+  const uint32_t my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t total_chunks = my_tiles * nk;
+  auto issue = [&](uint32_t g) {
+    const uint32_t t_iter = g / nk, chunk = g - t_iter * nk, slot = g % STAGES;
+    // the first chunk of a tile fetches its coordinates and parks them for everybody (read after a later barrier:
+    // at most ceil(STAGES / nk) <= 3 tiles are in flight, the ring holds 4)
+    uint2 rc;
+    if (chunk == 0) {
+      rc = __ldg(a.tile_table + blockIdx.x + t_iter * gridDim.x);
+      s_tile[t_iter & 3] = rc;
+    } else {
+      rc = s_tile[t_iter & 3];
     }
-    const uint32_t rb = a.rb_list[lo];
-    const uint32_t cb = max(rb, a.cb_min) + (tile - a.tile_prefix[lo]);
-    const uint4 *grow = a.planes + (size_t)rb * TILE;
-    const uint4 *gcol = a.planes + (size_t)cb * TILE;
-
-    auto issue = [&](uint32_t chunk, uint32_t slot) {
-      uint64_t *bar = &full[slot];
-      mbar_expect_tx(bar, 2u * STAGE_U4 * (uint32_t)sizeof(uint4));
-      uint4 *dr = srow + (size_t)slot * STAGE_U4;
-      uint4 *dc = scol + (size_t)slot * STAGE_U4;
+    const uint4 *grow = a.planes + (size_t)rc.x * TILE;
+    const uint4 *gcol = a.planes + (size_t)rc.y * TILE;
+    uint64_t *bar = &full[slot];
+    mbar_expect_tx(bar, 2u * STAGE_U4 * (uint32_t)sizeof(uint4));
+    uint4 *dr = srow + (size_t)slot * STAGE_U4;
+    uint4 *dc = scol + (size_t)slot * STAGE_U4;
 #pragma unroll
-      for (int kk = 0; kk < KC; ++kk) {
-        size_t goff = (size_t)(chunk * KC + kk) * a.Npad;
-        bulk_g2s(dr + kk * TILE, grow + goff, TILE * sizeof(uint4), bar);
-        bulk_g2s(dc + kk * TILE, gcol + goff, TILE * sizeof(uint4), bar);
-      }
-    };
-    if (tid == 0) {
-      for (uint32_t c = 0; c < (uint32_t)STAGES && c < nk; ++c) issue(c, (it + c) % STAGES);
+    for (int kk = 0; kk < KC; ++kk) {
+      const size_t goff = (size_t)(chunk * KC + kk) * a.Npad;
+      bulk_g2s(dr + kk * TILE, grow + goff, TILE * sizeof(uint4), bar);
+      bulk_g2s(dc + kk * TILE, gcol + goff, TILE * sizeof(uint4), bar);
     }
+  };
+  if (tid == 0)
+    for (uint32_t g = 0; g < (uint32_t)STAGES && g < total_chunks; ++g) issue(g);
+  __syncthreads();
+  uint32_t it = 0;  // running chunk counter
+  uint32_t t_iter = 0;
+
+  for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t_iter) {
+    const uint2 rc = s_tile[t_iter & 3];
+    const uint32_t rb = rc.x, cb = rc.y;
 
     uint32_t acc[8][8];
 #pragma unroll
@@ -730,12 +768,65 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
         }
       }
       __syncthreads();
-      if (tid == 0 && c + STAGES < nk) issue(c + STAGES, slot);
+      if (tid == 0 && it + STAGES < total_chunks) issue(it + STAGES);
     }
 
     // ---- epilogue: threshold + append -------------------------------------------------
     const uint32_t total_bits = a.Wp * 32u;
     const uint32_t lane = tid & 31;
+    // Most threads of a thresholded sweep hold no pair within the threshold (d = total_bits - matches): row maxima
+    // of the 8 x 8 match counts decide that with ~70 instructions instead of ~15 per pair. A warp without any hit
+    // skips the epilogue; a warp with a FEW hits lets just those lanes walk their qualifying rows and append with one
+    // atomic per lane (the order of the list is restored by the sort); a warp with many hits (unthresholded or
+    // dense output) takes the warp-aggregated path below.
+    uint32_t rmax[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t m = acc[i][0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) m = max(m, acc[i][j]);
+      rmax[i] = m;
+    }
+    uint32_t mx = rmax[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = max(mx, rmax[i]);
+    const bool hit = (int32_t)(total_bits - mx) <= a.dist;
+    const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit);
+    if (!hits) continue;
+    if (__popc(hits) <= 8) {
+      if (hit) {
+        uint32_t found = 0;
+        uint64_t keep1 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if ((int32_t)(total_bits - rmax[i]) <= a.dist) {
+            const uint32_t gi = rb * TILE + i * 16 + ty;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t gj = cb * TILE + j * 16 + tx;
+              const int32_t d = (int32_t)(total_bits - acc[i][j]);
+              if (gi < a.i_end && gj < a.n && gj > gi && gj >= a.j_start && d <= a.dist) {
+                keep1 |= 1ull << (i * 8 + j);
+                found++;
+              }
+            }
+          }
+        }
+        if (found) {
+          unsigned long long pos = atomicAdd(a.counter, (unsigned long long)found);
+          while (keep1) {
+            const int b = __ffsll((long long)keep1) - 1;
+            keep1 &= keep1 - 1;
+            if (pos < a.cap) {
+              a.keys[pos] = ((uint64_t)(rb * TILE + (b >> 3) * 16 + ty) << 32) | (cb * TILE + (b & 7) * 16 + tx);
+              a.dvals[pos] = total_bits - acc_at(acc, b);
+            }
+            pos++;
+          }
+        }
+      }
+      continue;
+    }
     uint32_t cnt = 0;
     uint64_t keep = 0;  // bit (i*8+j)
 #pragma unroll
@@ -1356,58 +1447,71 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   const TilePlan plan = plan_tiles(n, i_end, j_start, Npad, rank, world);
   const uint32_t n_cb = plan.n_cb, cb_min = plan.cb_min;
   const std::vector<uint32_t> &my_rb = plan.my_rb;
-  // bands: consecutive owned row-blocks whose pair count fits the edge buffer
-  const uint64_t CAP_MAX = 1ull << 28;
-  std::vector<std::pair<size_t, size_t>> bands;
-  std::vector<uint64_t> band_pairs;
-  {
+  // Units of work. A thresholded call first tries filter-and-refine over ALL owned row-blocks in one launch: the
+  // candidate list is bounded (CAND_CAP) because only a few per cent of the pairs may survive. Otherwise, or when the
+  // prefilter is not selective, the row-blocks are cut into bands whose pair count fits the edge buffer (a full-length
+  // sweep may emit every pair).
+  struct Unit { size_t first, last; uint64_t pairs; };
+  const uint64_t CAP_MAX = 1ull << 28, CAND_CAP = 1ull << 26;
+  uint64_t total_pairs = 0, total_tiles = 0;
+  for (size_t k = 0; k < my_rb.size(); ++k) {
+    total_pairs += plan.rb_pairs[k];
+    total_tiles += n_cb - std::max(my_rb[k], cb_min);
+  }
+  S.n_pairs += total_pairs;
+  auto make_units = [&](uint64_t limit, uint64_t tile_limit) {
+    std::vector<Unit> u;
     size_t b0 = 0;
-    uint64_t acc = 0;
+    uint64_t acc = 0, tiles = 0;
     for (size_t k = 0; k < my_rb.size(); ++k) {
-      uint64_t p = plan.rb_pairs[k];
-      S.n_pairs += p;
-      if (k > b0 && acc + p > CAP_MAX) {
-        bands.push_back({b0, k});
-        band_pairs.push_back(acc);
+      const uint64_t p = plan.rb_pairs[k], t = n_cb - std::max(my_rb[k], cb_min);
+      if (k > b0 && (acc + p > limit || tiles + t > tile_limit)) {
+        u.push_back({b0, k, acc});
         b0 = k;
         acc = 0;
+        tiles = 0;
       }
       acc += p;
+      tiles += t;
     }
-    if (b0 < my_rb.size()) {
-      bands.push_back({b0, my_rb.size()});
-      band_pairs.push_back(acc);
-    }
-  }
-  if (bands.empty()) {
+    if (b0 < my_rb.size()) u.push_back({b0, my_rb.size(), acc});
+    return u;
+  };
+  if (my_rb.empty()) {
     S.ms_total = Ttot.stop();
     return;
   }
-  uint64_t cap = 0;
-  for (uint64_t p : band_pairs) cap = std::max(cap, p);
-  cap = std::max<uint64_t>(cap, 1);
+  const bool tc_ok = o.sweep_variant != 1 && !ing.partial_ambiguity;  // tensor cores unless forced off / inapplicable
+  bool prefilter_mode = o.sweep_variant == 0 && o.dist >= 0 && (uint64_t)o.dist < (uint64_t)PREFILTER_WORDS * 32 &&
+                        Wp >= 4 * PREFILTER_WORDS && total_tiles < (1ull << 31);
 
-  DevBuf<uint64_t> keys(cap), keys2(cap);
-  DevBuf<uint32_t> dv(cap), dv2(cap);
   DevBuf<unsigned long long> counter(1);
   DevBuf<uint32_t> d_rb(my_rb.size()), d_prefix(my_rb.size() + 1);
-  size_t sort_tmp_bytes = 0;
   int end_bit = 32;
   while ((1ull << (end_bit - 32)) < n) end_bit++;
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, keys.p, keys2.p, dv.p, dv2.p, (int64_t)cap, 0, end_bit, st);
-  DevBuf<uint8_t> sort_tmp(sort_tmp_bytes);
 
   // ---- fused transmission likelihood set-up (device table over (d, day difference)) ----------
   TransLut lut;
   const bool fuse_trans = lut.setup(o, n, (uint64_t)std::min<int64_t>(std::max<int64_t>(o.dist, 0), (int64_t)Wp * 32) + 1, st);
   if (fuse_trans) out.has_trans = true;
 
-  for (size_t b = 0; b < bands.size(); ++b) {
-    std::vector<uint32_t> rbs(my_rb.begin() + bands[b].first, my_rb.begin() + bands[b].second);
+  for (int pass = 0; pass < 2; ++pass) {
+  const std::vector<Unit> units = prefilter_mode ? std::vector<Unit>{{0, my_rb.size(), total_pairs}} : make_units(CAP_MAX, 1ull << 31);
+  uint64_t cap = 1;
+  for (const Unit &u : units) cap = std::max(cap, u.pairs);
+  if (prefilter_mode) cap = std::min(cap, CAND_CAP);
+  DevBuf<uint64_t> keys(cap), keys2(cap);
+  DevBuf<uint32_t> dv(cap), dv2(cap);
+  size_t sort_tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, keys.p, keys2.p, dv.p, dv2.p, (int64_t)cap, 0, end_bit, st);
+  DevBuf<uint8_t> sort_tmp(sort_tmp_bytes);
+  bool fall_back = false;
+
+  for (size_t b = 0; b < units.size(); ++b) {
+    std::vector<uint32_t> rbs(my_rb.begin() + units[b].first, my_rb.begin() + units[b].last);
     std::vector<uint32_t> prefix(rbs.size() + 1, 0);
     for (size_t k = 0; k < rbs.size(); ++k) prefix[k + 1] = prefix[k] + (n_cb - std::max(rbs[k], cb_min));
     const uint32_t n_tiles = prefix.back();
-    S.n_tiles += n_tiles;
     TRACS_CK(cudaMemcpyAsync(d_rb.p, rbs.data(), rbs.size() * 4, cudaMemcpyHostToDevice, st));
     TRACS_CK(cudaMemcpyAsync(d_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, st));
     TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
@@ -1416,52 +1520,61 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     a.j_start = (uint32_t)j_start; a.dist = o.dist; a.rb_list = d_rb.p; a.tile_prefix = d_prefix.p;
     a.n_rb = (uint32_t)rbs.size(); a.n_tiles = n_tiles; a.cb_min = cb_min; a.counter = counter.p;
     a.keys = keys.p; a.dvals = dv.p; a.cap = cap; a.one = 1;
-    const bool tc_ok = o.sweep_variant != 1 && !ing.partial_ambiguity;  // tensor cores unless forced off / inapplicable
+    DevBuf<uint2> d_table(std::max<uint32_t>(1, n_tiles));
+    if (n_tiles) {
+      k_tile_table<<<(n_tiles + 255) / 256, 256, 0, st>>>(d_rb.p, d_prefix.p, a.n_rb, cb_min, n_tiles, d_table.p);
+      S.kernel_launches++;
+    }
+    a.tile_table = d_table.p;
     auto read_counter = [&]() -> unsigned long long {
       unsigned long long c = 0;
       TRACS_CK(cudaMemcpyAsync(&c, counter.p, sizeof c, cudaMemcpyDeviceToHost, st));
       TRACS_CK(cudaStreamSynchronize(st));
       return c;
     };
-    // Filter-and-refine for thresholded sweeps: tile-sweep only the first PREFILTER_WORDS words; a
-    // pair whose partial distance already exceeds `dist` is decided. If few pairs survive, finish
-    // those per pair (k_refine); otherwise fall back to the full-length tile sweep.
     unsigned long long E = 0;
-    bool refined = false;
-    const bool try_prefilter = o.sweep_variant == 0 && o.dist >= 0 && (uint64_t)o.dist < (uint64_t)PREFILTER_WORDS * 32 &&
-                               Wp >= 4 * PREFILTER_WORDS;
-    // narrow window first (a quarter of the work when it is enough), the widest one if too many pairs survive it
-    for (uint32_t pw = try_prefilter ? prefilter_words(o.dist) : 0; pw && !refined; pw = pw < PREFILTER_WORDS ? PREFILTER_WORDS : 0) {
-      a.Wp = pw;
-      T.start();
-      launch_tile_sweep(a, tc_ok, st);
-      S.ms_sweep += T.stop();
-      S.swept_wordpairs += band_pairs[b] * pw;
-      const unsigned long long n_cand = read_counter();
-      if (n_cand > cap) throw std::runtime_error("internal error: edge buffer overflow");
-      if (n_cand * 25 <= band_pairs[b]) {  // <= 4 % survive: per-pair refinement is cheaper than tiles
-        refined = true;
-        S.n_candidates += n_cand;
+    if (prefilter_mode) {
+      // Filter-and-refine: tile-sweep only the first words of every pair; d is monotone in the number of sites, so a
+      // pair whose partial distance already exceeds `dist` is decided. Windows of 8, 16 and 64 words are tried in turn
+      // until <= 4 % of the pairs survive; those are finished per pair (k_refine). If even the widest window is not
+      // selective the call falls back to banded full-length sweeps (cost of the failed attempts: 88 / Wp).
+      // Short windows run on the LOP3/POPC kernel (the tensor-core kernel pays its per-tile pipeline fill and its
+      // TMEM epilogue on every 128 x 128 tile: measured equal at 16 words, slower below), the 64-word one on the
+      // tensor cores when the masks allow it.
+      bool refined = false;
+      const uint32_t first = o.dist < 32 ? 8u : prefilter_words(o.dist);
+      for (uint32_t pw = first; pw && !refined; pw = pw < 16 ? 16 : (pw < PREFILTER_WORDS ? PREFILTER_WORDS : 0)) {
+        a.Wp = pw;
+        T.start();
+        launch_tile_sweep(a, tc_ok && pw > 16, st);
+        S.ms_sweep += T.stop();
+        S.n_tiles += n_tiles;
+        S.swept_wordpairs += units[b].pairs * pw;
+        const unsigned long long n_cand = read_counter();
         TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
-        if (n_cand) {
-          T.start();
-          k_refine<<<(unsigned)((n_cand * 32 + 255) / 256), 256, 0, st>>>(keys.p, dv.p, n_cand, planesT.p, Wp, pw, o.dist, counter.p,
-                                                                       keys2.p, dv2.p);
-          S.kernel_launches++;
-          TRACS_CK(cudaGetLastError());
-          S.ms_refine += T.stop();
-          E = read_counter();
+        if (n_cand <= cap && n_cand * 25 <= units[b].pairs) {  // <= 4 % survive: per-pair refinement is cheaper than tiles
+          refined = true;
+          S.n_candidates += n_cand;
+          if (n_cand) {
+            T.start();
+            k_refine<<<(unsigned)((n_cand * 32 + 255) / 256), 256, 0, st>>>(keys.p, dv.p, n_cand, planesT.p, Wp, pw, o.dist, counter.p,
+                                                                         keys2.p, dv2.p);
+            S.kernel_launches++;
+            TRACS_CK(cudaGetLastError());
+            S.ms_refine += T.stop();
+            E = read_counter();
+          }
+          std::swap(keys.p, keys2.p);  // survivors now in (keys, dv) like the plain sweep leaves them
+          std::swap(dv.p, dv2.p);
+        } else if (pw == PREFILTER_WORDS) {
+          S.n_candidates += n_cand;
         }
-        std::swap(keys.p, keys2.p);  // survivors now in (keys, dv) like the plain sweep leaves them
-        std::swap(dv.p, dv2.p);
-      } else {
-        if (pw == PREFILTER_WORDS) S.n_candidates += n_cand;
-        TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
       }
-    }
-    if (!refined) {
-      a.Wp = Wp;
-      a.keys = keys.p; a.dvals = dv.p;
+      if (!refined) {
+        fall_back = true;
+        break;
+      }
+    } else {
       // full-length sweep: the tensor-core kernel (2.0x the LOP3/POPC kernel at C2, profiles/r1_tc_ncu.md) whenever
       // the masks allow its identity; variant 1 forces the LOP3/POPC kernel, variant 2 insists on tensor cores
       if (o.sweep_variant == 2 && ing.partial_ambiguity)
@@ -1469,7 +1582,8 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       T.start();
       launch_tile_sweep(a, tc_ok, st);
       S.ms_sweep += T.stop();
-      S.swept_wordpairs += band_pairs[b] * std::max<uint64_t>(W, 1);  // algorithmic words (padding not counted)
+      S.n_tiles += n_tiles;
+      S.swept_wordpairs += units[b].pairs * std::max<uint64_t>(W, 1);  // algorithmic words (padding not counted)
       E = read_counter();
     }
     if (E > cap) throw std::runtime_error("internal error: edge buffer overflow");
@@ -1608,7 +1722,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       TRACS_CK(cudaGetLastError());
       S.ms_ncomp += T.stop();
     }
-    if (o.keep_on_device && bands.size() == 1) {
+    if (o.keep_on_device && units.size() == 1) {
       void *dp = nullptr;
       TRACS_CK(cudaMalloc(&dp, std::max<size_t>(32, 32 * E)));
       out.dev_packed = dp;
@@ -1625,6 +1739,9 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     S.ms_d2h += T.stop();
     S.d2h_bytes += E * 8 * (want_n ? 4 : 3);
     S.n_edges += E;
+  }
+  if (!fall_back) break;
+  prefilter_mode = false;  // second pass: banded full-length sweeps
   }
   S.ms_total = Ttot.stop();
 }

@@ -65,14 +65,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(const SweepArgs a) {
   uint32_t it = 0;           // running word counter (stage = it % TC_STAGES)
   uint32_t tile_iter = 0;
 
+  uint2 rc_next = blockIdx.x < a.n_tiles ? __ldg(a.tile_table + blockIdx.x) : make_uint2(0, 0);
   for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_iter) {
-    uint32_t lo = 0, hi = a.n_rb;
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (a.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
-    }
-    const uint32_t rb = a.rb_list[lo];
-    const uint32_t cb = max(rb, a.cb_min) + (tile - a.tile_prefix[lo]);
+    const uint32_t rb = rc_next.x, cb = rc_next.y;
+    if (tile + gridDim.x < a.n_tiles) rc_next = __ldg(a.tile_table + tile + gridDim.x);  // in flight during this tile
 
     if (warp < TC_PRODUCERS / 32) {
       // ===== producers: bit-planes -> int8 operands in the UMMA layout =====

@@ -93,23 +93,42 @@ def exchange_candidates(torch, dist_mod, device, world, mine):
 
 
 def sweep(torch, dist_mod, device, rank, world, slab_ptr, n, L_slab, pitch, L_total, dist, days=None, lamb=29.903, beta=73.0,
-          threshold_Ek=0.01, packed=False, backend=None):
-    """All ranks call this. Returns (edge table on rank 0 / None elsewhere, per-rank stats dict)."""
+          threshold_Ek=0.01, packed=False, backend=None, profile=False):
+    """All ranks call this. Returns (edge table on rank 0 / None elsewhere, per-rank stats dict).
+    profile=True adds host wall-clock times of the phases (each closed by a device synchronise: slower, diagnosis only)."""
+    import time
     be = backend if backend is not None else LibBackend(torch, device, slab_ptr, n, L_slab, pitch, packed)
+    marks = []
+
+    def mark(name):
+        if profile:
+            if device.type == "cuda":
+                torch.cuda.synchronize(device)
+            marks.append((name, time.perf_counter()))
     try:
+        mark("start")
         mine, st_open = be.open(dist, rank, world)
+        mark("open")
         keys = exchange_candidates(torch, dist_mod, device, world, mine)
+        mark("exchange")
         E = int(keys.numel())
         both = torch.zeros((2, max(E, 1)), dtype=torch.int32, device=device)
         st_part = be.partials(keys, both[0], both[1])
+        mark("partials")
         if world > 1:
             dist_mod.all_reduce(both)
+        mark("allreduce")
         stats = dict(st_open)
         stats.update(st_part)   # the library's counters run on from open() through partials()
         stats["n_candidates_all"] = E
+        if profile:
+            stats["phases_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks, marks[1:])}
         if rank != 0:
             return None, stats
         res, st_fin = be.finish(keys, both[0], both[1], L_total, dist, days, lamb, beta, threshold_Ek)
+        mark("finish")
+        if profile:
+            stats["phases_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks, marks[1:])}
         stats["kernel_launches"] = stats.get("kernel_launches", 0) + st_fin.get("kernel_launches", 0)
         for k in ("ms_trans", "ms_d2h", "d2h_bytes", "n_edges"):
             stats[k] = st_fin.get(k, 0)
