@@ -1,0 +1,88 @@
+"""GPU parity of the candidate-pair evaluation (csrc/pairs.inl): connected components of the candidate graph,
+dense components as 64 x 64 member blocks (k_block_d, k_block_n), sparse ones per candidate (k_pairs_sparse) --
+against the oracle and against the per-candidate kernel forced for everything (TRACS_PAIRS=sparse)."""
+import numpy as np
+import pytest
+
+import tracs_b200
+from tracs_b200 import synth
+
+pytestmark = pytest.mark.gpu
+COLS = ("rows", "cols", "dist", "ncomp")
+
+
+def _cmp(res, orc):
+    r, c, d, f, nn = orc
+    assert res["rows"].tolist() == r.tolist()
+    assert res["cols"].tolist() == c.tolist()
+    assert res["dist"].tolist() == d.tolist()
+    assert res["ncomp"].tolist() == nn.tolist()
+
+
+def _both_ways(s, dist, monkeypatch, oracle_mod, **kw):
+    orc = oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=8)
+    res = tracs_b200.pairsnp_matrix(s, dist=dist, **kw)
+    st = tracs_b200.last_stats()
+    assert st["ms_refine"] > 0, "the filter-and-refine path is the one under test"
+    _cmp(res, orc)
+    monkeypatch.setenv("TRACS_PAIRS", "sparse")
+    ref = tracs_b200.pairsnp_matrix(s, dist=dist, **kw)
+    monkeypatch.delenv("TRACS_PAIRS")
+    for k in COLS:
+        assert res[k].tolist() == ref[k].tolist()
+    return res, orc
+
+
+@pytest.mark.parametrize("n,n_clusters,big", [(300, 60, 0), (1500, 300, 200), (1600, 30, 0), (520, 520, 0), (1400, 200, 150)])
+def test_component_blocks_match_oracle(oracle_mod, monkeypatch, n, n_clusters, big):
+    """Cliques of ~5 and ~53 members, all singletons (no candidates), and -- `big` -- one clique of 200 / 150 members
+    scattered over the sample range (several 64 x 64 blocks per component, off-diagonal blocks included) next to small
+    ones; N-rich rows and gap runs so that the N intersections are not trivial."""
+    s = synth.generate(n, 200_000, p_var=0.06, n_clusters=n_clusters, mu=4, p_N=0.01, p_amb=0.01, seed=7 + n_clusters, gaps=4)
+    if big:
+        rng = np.random.default_rng(big)
+        who = rng.choice(n, size=big, replace=False)
+        var = np.nonzero((s != s[0]).any(axis=0))[0]
+        for k in who[1:]:                     # copies of one sample with a few private substitutions each
+            s[k] = s[who[0]]
+            for t in rng.choice(var, size=3, replace=False):
+                s[k, t] = ord("A") if s[k, t] != ord("A") else ord("G")
+        s[rng.random(s.shape) < 0.01] = ord("N")
+    res, orc = _both_ways(s, 20, monkeypatch, oracle_mod)
+    if n_clusters < n:
+        assert len(res["rows"]) > n
+    if big:
+        assert len(res["rows"]) > big * (big - 1) // 2
+
+
+def test_sparse_components_take_the_per_candidate_kernel(oracle_mod, monkeypatch):
+    """A chain (every sample within the threshold of its two neighbours only) is one large, sparse component: it
+    must not be evaluated as m x m blocks; mixed with small cliques in the same alignment."""
+    n, L = 400, 200_000
+    s = synth.generate(n, L, p_var=0.06, n_clusters=40, mu=3, p_N=0.005, seed=99, gaps=2)
+    rng = np.random.default_rng(5)
+    sites = rng.choice(L, size=100 * 12, replace=False)
+    for k in range(1, 100):            # samples 0..99: s_k = s_0 + 12 k substitutions  =>  d(s_a, s_b) = 12 |a - b|
+        s[k] = s[0]
+        for t in sites[:12 * k]:
+            s[k, t] = ord("A") if s[0, t] != ord("A") else ord("C")
+    res, orc = _both_ways(s, 20, monkeypatch, oracle_mod)
+    chain = [(int(a), int(b)) for a, b in zip(res["rows"], res["cols"]) if b < 100]
+    assert (0, 1) in chain and (98, 99) in chain and (0, 2) not in chain and len(chain) == 99
+
+
+def test_blocks_with_fused_likelihood_and_two_file_ranges(oracle_mod, monkeypatch):
+    s = synth.generate(500, 150_000, p_var=0.08, n_clusters=25, mu=4, p_N=0.01, seed=31, gaps=3)
+    days = np.random.default_rng(1).integers(0, 120, size=500).astype(np.int32)
+    res, orc = _both_ways(s, 25, monkeypatch, oracle_mod, days=days)
+    r, c, d = orc[0], orc[1], orc[2]
+    dt = np.abs(days[r.astype(int)] * 86400.0 - days[c.astype(int)] * 86400.0) / 31556952.0
+    op0, oeK = oracle_mod.trans_dist(d.astype(np.int32), dt, 29.903, 73.0, 0.01)
+    assert np.allclose(res["p0_log"], op0, rtol=1e-6, atol=0)
+    pos = dt > 0
+    assert np.allclose(res["eK"][pos], oeK[pos], rtol=1e-6, atol=0)
+    for n1 in (100, 257):
+        got = tracs_b200.pairsnp_matrix(s, dist=25, i_end=n1, j_start=n1)
+        _cmp(got, oracle_mod.pairsnp_ascii(s, i_end=n1, j_start=n1, dist=25, n_threads=4))
+    got = tracs_b200.pairsnp_matrix(s, dist=25, want_ncomp=False)
+    assert got["rows"].tolist() == r.tolist() and got["dist"].tolist() == d.tolist() and not got["ncomp"].any()

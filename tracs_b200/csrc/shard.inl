@@ -7,7 +7,7 @@
 //      (a partial distance over any subset of sites is a lower bound of d, so pairs it rejects are
 //      decided for good);                                              -> candidate pairs (few)
 //   2. the candidate lists are all-gathered (the caller does this with NCCL);
-//   3. every rank evaluates its slab's partial d and |N_i u N_j| for ALL candidates;  [this file]
+//   3. every rank evaluates its slab's partial d and |N_i u N_j| for ALL candidates;  [pairs.inl]
 //   4. the two integer vectors are all-reduced (sum) and thresholded by the caller.
 // No bit-plane or N-plane ever crosses NVLink; traffic is O(candidates).
 // Reference semantics unchanged: src/pairsnp.hpp:398-403 (d), :417-419 (compared sites).
@@ -19,48 +19,6 @@ struct SiteShard {
   DevBuf<uint64_t> cand;   // candidate keys (i << 32 | j) found by this rank, sorted
   uint64_t n_cand = 0;
 };
-
-// one warp per candidate: mismatches over ALL local words, and |N_i u N_j| over the local slab
-__global__ void __launch_bounds__(256)
-k_shard_partials(const uint64_t *__restrict__ keys, uint64_t n_keys, const uint4 *__restrict__ planesT, uint32_t Wp,
-                 const uint32_t *__restrict__ nplane, uint64_t npitch, const uint8_t *__restrict__ nsum, uint64_t spitch,
-                 const uint32_t *__restrict__ ncount, uint32_t *__restrict__ d_out, uint32_t *__restrict__ u_out) {
-  const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t lane = threadIdx.x & 31;
-  if (e >= n_keys) return;
-  const uint64_t k = keys[e];
-  const uint64_t i = k >> 32, j = k & 0xFFFFFFFFull;
-  const uint4 *ri = planesT + i * Wp, *rj = planesT + j * Wp;
-  uint32_t mism = 0;
-#pragma unroll 4
-  for (uint32_t w = lane; w < Wp; w += 32) {
-    const uint4 x = __ldg(ri + w), y = __ldg(rj + w);
-    mism += __popc(~((x.x & y.x) | (x.y & y.y) | (x.z & y.z) | (x.w & y.w)));
-  }
-  const uint32_t *si = reinterpret_cast<const uint32_t *>(nsum + i * spitch);
-  const uint32_t *sj = reinterpret_cast<const uint32_t *>(nsum + j * spitch);
-  const uint4 *ni = reinterpret_cast<const uint4 *>(nplane + i * npitch);
-  const uint4 *nj = reinterpret_cast<const uint4 *>(nplane + j * npitch);
-  uint32_t inter = 0;
-  for (uint64_t q = lane; q < spitch / 4; q += 32) {
-    uint32_t m = __ldg(si + q) & __ldg(sj + q);
-    while (m) {
-      const uint32_t b = __ffs(m) - 1;
-      m &= m - 1;
-      const uint4 x = __ldg(ni + q * 32 + b), y = __ldg(nj + q * 32 + b);
-      inter += __popc(x.x & y.x) + __popc(x.y & y.y) + __popc(x.z & y.z) + __popc(x.w & y.w);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mism += __shfl_xor_sync(0xFFFFFFFFu, mism, o);
-    inter += __shfl_xor_sync(0xFFFFFFFFu, inter, o);
-  }
-  if (lane == 0) {
-    d_out[e] = mism;
-    u_out[e] = ncount[i] + ncount[j] - inter;
-  }
-}
 
 // finish: candidates with summed d <= dist, in key order
 __global__ void k_finish_flags(const uint32_t *__restrict__ d, uint64_t n, int32_t dist, uint8_t *__restrict__ flags) {
@@ -80,19 +38,24 @@ __global__ void k_finish_gather(const uint32_t *__restrict__ idx, const uint64_t
   rows[e] = k >> 32;
   cols[e] = k & 0xFFFFFFFFull;
   dist[e] = d[c];
-  ncomp[e] = L_total - u[c];
+  if (u) ncomp[e] = L_total - u[c];
 }
 
-// summed candidate vectors (device) -> edge columns on the host
-void site_shard_finish_device(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
-                              uint64_t L_total, const tracs_opts_t &o, HostEdges &out, cudaStream_t st) {
+// Candidate vectors (device; keys ascending, d = full-length distance, union = |N_i u N_j| or null) -> edge columns on
+// the host: threshold, compared sites, fused likelihood. Shared by the single-GPU filter-and-refine path and by
+// the last step of the site-sharded sweep.
+static void finish_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
+                              uint64_t L_total, const tracs_opts_t &o, TransLut *lut_in, HostEdges &out, cudaStream_t st) {
   tracs_stats_t &S = g_stats;
   if (n_keys == 0) return;
-  if (n_keys >= (1ull << 32)) throw std::runtime_error("site shard: too many candidates");
+  if (n_keys >= (1ull << 32)) throw std::runtime_error("too many candidates");
   Timer T(st);
   T.start();
-  TransLut lut;
-  const bool fuse = lut.setup(o, n, (uint64_t)std::max<int64_t>(o.dist, 0) + 1, st);
+  TransLut lut_own;
+  bool fuse = lut_in != nullptr;
+  if (!fuse) fuse = lut_own.setup(o, n, (uint64_t)std::max<int64_t>(o.dist, 0) + 1, st);
+  TransLut &lut = lut_in ? *lut_in : lut_own;
+  const bool want_n = dev_union != nullptr;
   DevBuf<uint8_t> flags(n_keys);
   DevBuf<uint32_t> idx(n_keys);
   DevBuf<uint64_t> n_sel(1);
@@ -113,30 +76,37 @@ void site_shard_finish_device(const uint64_t *dev_keys, const uint32_t *dev_d, c
   TRACS_CK(cudaMemcpyAsync(&E, n_sel.p, 8, cudaMemcpyDeviceToHost, st));
   TRACS_CK(cudaStreamSynchronize(st));
   S.ms_sort += T.stop();
-  S.n_edges = E;
+  S.n_edges += E;
   if (E == 0) return;
-  out.rows.resize(E); out.cols.resize(E); out.dist.resize(E); out.ncomp.resize(E);
-  TRACS_CK(cudaMemcpyAsync(out.rows.data(), d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
-  TRACS_CK(cudaMemcpyAsync(out.cols.data(), d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));
-  TRACS_CK(cudaMemcpyAsync(out.dist.data(), d_dist.p, E * 8, cudaMemcpyDeviceToHost, st));
-  TRACS_CK(cudaMemcpyAsync(out.ncomp.data(), d_nc.p, E * 8, cudaMemcpyDeviceToHost, st));
-  S.d2h_bytes += E * 32;
+  const size_t old = out.rows.size();
+  out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E);
+  if (want_n) out.ncomp.resize(old + E);
+  TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
+  TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));
+  TRACS_CK(cudaMemcpyAsync(out.dist.data() + old, d_dist.p, E * 8, cudaMemcpyDeviceToHost, st));
+  if (want_n) TRACS_CK(cudaMemcpyAsync(out.ncomp.data() + old, d_nc.p, E * 8, cudaMemcpyDeviceToHost, st));
+  S.d2h_bytes += E * (want_n ? 32 : 24);
   DevBuf<double> d_p0, d_eK, d_dt;
   if (fuse) {
     T.start();
     out.has_trans = true;
     d_p0.alloc(E); d_eK.alloc(E); d_dt.alloc(E);
-    out.p0_log.resize(E); out.eK.resize(E); out.datediff.resize(E);
+    out.p0_log.resize(old + E); out.eK.resize(old + E); out.datediff.resize(old + E);
     lut.apply(keys_o.p, d_o.p, E, d_p0.p, d_eK.p, d_dt.p, st);
     S.ms_trans += T.stop();
-    TRACS_CK(cudaMemcpyAsync(out.p0_log.data(), d_p0.p, E * 8, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaMemcpyAsync(out.eK.data(), d_eK.p, E * 8, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaMemcpyAsync(out.datediff.data(), d_dt.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(out.p0_log.data() + old, d_p0.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(out.eK.data() + old, d_eK.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(out.datediff.data() + old, d_dt.p, E * 8, cudaMemcpyDeviceToHost, st));
     S.d2h_bytes += E * 24;
   }
   T.start();
   TRACS_CK(cudaStreamSynchronize(st));
   S.ms_d2h += T.stop();
+}
+
+void site_shard_finish_device(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
+                              uint64_t L_total, const tracs_opts_t &o, HostEdges &out, cudaStream_t st) {
+  finish_candidates(dev_keys, dev_d, dev_union, n_keys, n, L_total, o, nullptr, out, st);
 }
 
 }  // namespace tracs
@@ -258,10 +228,7 @@ int tracs_site_shard_partials(void *handle, const uint64_t *dev_keys, size_t n_k
     if (!n_keys) return;
     Timer T(0);
     T.start();
-    k_shard_partials<<<(unsigned)(((uint64_t)n_keys * 32 + 255) / 256), 256>>>(dev_keys, n_keys, g.planesT.p, g.Wp, g.nplane.p, g.npitch,
-                                                                            g.nsum.p, g.spitch, g.ncount.p, dev_d, dev_union);
-    g_stats.kernel_launches++;
-    TRACS_CK(cudaGetLastError());
+    eval_pairs(g, dev_keys, n_keys, dev_d, dev_union, 0);
     g_stats.ms_refine += T.stop();
   });
 }

@@ -39,7 +39,7 @@ static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m
 //   Two adjacent words of one sample (8 sites) share one selector register: nibble 2k = word 0
 //   byte k, nibble 2k+1 = word 1 byte k, so every lookup result holds sites (0, 4, 1, 5) or
 //   (2, 6, 3, 7) of the 8-site group. The N-plane word is stored in that fixed site permutation:
-//   its only consumers are population counts of ANDs (k_ncomp, k_shard_partials).
+//   its only consumers are population counts of ANDs (k_ncomp, k_block_n, k_pairs_sparse).
 // ------------------------------------------------------------------------------------------
 constexpr int PACK_THREADS = 256;
 constexpr int PACK_SCHUNK = 256;
@@ -1420,6 +1420,13 @@ static TilePlan plan_tiles(uint64_t n, uint64_t i_end, uint64_t j_start, uint32_
   return p;
 }
 
+}  // namespace tracs
+#include "pairs.inl"
+namespace tracs {
+
+static void finish_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
+                              uint64_t L_total, const tracs_opts_t &o, TransLut *lut_in, HostEdges &out, cudaStream_t st);
+
 // Sweeps the device-resident ASCII matrix and appends edges (sorted) to `out`.
 void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,
                   HostEdges &out, cudaStream_t st) {
@@ -1533,6 +1540,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       return c;
     };
     unsigned long long E = 0;
+    bool handled = false;
     if (prefilter_mode) {
       // Filter-and-refine: tile-sweep only the first words of every pair; d is monotone in the number of sites, so a
       // pair whose partial distance already exceeds `dist` is decided. Windows of 8, 16 and 64 words are tried in turn
@@ -1555,7 +1563,21 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
         if (n_cand <= cap && n_cand * 25 <= units[b].pairs) {  // <= 4 % survive: per-pair refinement is cheaper than tiles
           refined = true;
           S.n_candidates += n_cand;
-          if (n_cand) {
+          if (n_cand && !o.filter) {
+            // candidates in key order -> full-length d and |N u N| per candidate (component blocks, pairs.inl) ->
+            // threshold, compared sites, likelihood and the copy to the host in one go (the tail below is skipped)
+            T.start();
+            size_t kb = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, kb, keys.p, keys2.p, (int64_t)n_cand, 0, end_bit, st);
+            if (kb > sort_tmp_bytes) throw std::runtime_error("internal error: sort scratch too small");
+            cub::DeviceRadixSort::SortKeys(sort_tmp.p, kb, keys.p, keys2.p, (int64_t)n_cand, 0, end_bit, st);
+            S.kernel_launches += 2 + (end_bit + 7) / 8;
+            DevBuf<uint32_t> u_full(want_n ? n_cand : 1);
+            eval_pairs(ing, keys2.p, n_cand, dv2.p, want_n ? u_full.p : nullptr, st);
+            S.ms_refine += T.stop();
+            finish_candidates(keys2.p, dv2.p, want_n ? u_full.p : nullptr, n_cand, n, L, o, fuse_trans ? &lut : nullptr, out, st);
+            handled = true;
+          } else if (n_cand) {
             T.start();
             k_refine<<<(unsigned)((n_cand * 32 + 255) / 256), 256, 0, st>>>(keys.p, dv.p, n_cand, planesT.p, Wp, pw, o.dist, counter.p,
                                                                          keys2.p, dv2.p);
@@ -1574,6 +1596,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
         fall_back = true;
         break;
       }
+      if (handled) continue;
     } else {
       // full-length sweep: the tensor-core kernel (2.0x the LOP3/POPC kernel at C2, profiles/r1_tc_ncu.md) whenever
       // the masks allow its identity; variant 1 forces the LOP3/POPC kernel, variant 2 insists on tensor cores
