@@ -36,7 +36,7 @@ typedef struct tracs_edges {
   uint64_t *rows;    /* sample index i                                   */
   uint64_t *cols;    /* sample index j                                   */
   uint64_t *dist;    /* SNP distance d(i,j)                              */
-  uint64_t *filt;    /* recombination-filtered distance (zeros if !filter) */
+  uint64_t *filt;    /* recombination-filtered distance; NULL when the filter is off (= the reference's vector of zeros) */
   uint64_t *ncomp;   /* compared (non-N) sites                           */
   double *p0_log;    /* log P(direct transmission)   or NULL             */
   double *eK;        /* E[# intermediate hosts]       or NULL             */
@@ -186,6 +186,16 @@ int tracs_site_shard_partials(void *handle, const uint64_t *dev_keys, size_t n_k
  * shard is read). Output as tracs_pairsnp_device. */
 int tracs_site_shard_finish(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, size_t n_keys,
                             size_t n_samples, size_t L_total, const tracs_opts_t *opts, tracs_edges_t *out);
+/* The same last step split in two, for N > 1: every rank takes a contiguous slice of the summed candidate vectors.
+ * _select thresholds the slice and returns how many edges it holds (the selected columns stay on the device, owned by
+ * *selection); the caller exchanges the counts (all-gather) to learn where each slice starts in the edge table;
+ * _emit computes the likelihood columns and copies everything into the caller's HOST columns (dst->rows ... datediff:
+ * page-locked or tracs_host_register'ed memory, e.g. one shared-memory segment mapped by all ranks) starting at
+ * element `at`, then releases the selection. So each GPU delivers its share over its own PCIe link. dst->filt, names
+ * and counts are not touched; dst->ncomp / p0_log / eK / datediff may be NULL when not wanted. */
+int tracs_site_shard_select(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, size_t n_keys,
+                            size_t n_samples, size_t L_total, const tracs_opts_t *opts, void **selection, size_t *n_selected);
+int tracs_site_shard_emit(void *selection, const tracs_edges_t *dst, size_t at, int *has_trans);
 int tracs_site_shard_close(void *handle);
 
 /* Single-linkage clusters of the thresholded edge list = connected components (what tracs/cluster.py:126-129
@@ -238,6 +248,9 @@ int tracs_dev_alloc(void **p, size_t bytes);
 int tracs_dev_free(void *p);
 int tracs_host_alloc_pinned(void **p, size_t bytes);
 int tracs_host_free_pinned(void *p);
+/* page-locks an existing host range (e.g. a shared-memory mapping) for direct device copies / releases it */
+int tracs_host_register(void *p, size_t bytes);
+int tracs_host_unregister(void *p);
 int tracs_memcpy_d2h(void *dst, const void *src, size_t bytes);
 int tracs_memcpy_h2d(void *dst, const void *src, size_t bytes);
 

@@ -91,6 +91,15 @@ class _OracleBackend:
         return {"rows": k[keep] >> np.uint64(32), "cols": k[keep] & np.uint64(0xFFFFFFFF), "dist": dn[:len(k)][keep].astype(np.uint64),
                 "ncomp": (L_total - un[:len(k)][keep].astype(np.int64)).astype(np.uint64)}, {"kernel_launches": 3, "n_edges": int(keep.sum())}
 
+    def select(self, keys, d, u, L_total, dist, days, lamb, beta, threshold_Ek):
+        res, st = self.finish(keys, d, u, L_total, dist, days, lamb, beta, threshold_Ek)
+        return res, len(res["rows"]), {"kernel_launches": 3}
+
+    def emit(self, sel, table, at):
+        for c in ("rows", "cols", "dist", "ncomp"):
+            table.views[c][at:at + len(sel[c])] = sel[c]
+        return False, {"kernel_launches": 1}
+
     def close(self):
         pass
 

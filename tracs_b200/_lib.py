@@ -53,7 +53,8 @@ SYMBOLS = ["tracs_pairsnp", "tracs_pairsnp_host", "tracs_pairsnp_device", "tracs
            "tracs_dev_free", "tracs_host_alloc_pinned", "tracs_host_free_pinned", "tracs_memcpy_d2h",
            "tracs_memcpy_h2d", "tracs_int_peak", "tracs_read_fasta", "tracs_free_fasta", "tracs_shard_rowblocks",
            "tracs_site_shard_open", "tracs_site_shard_partials", "tracs_site_shard_close", "tracs_connected_components",
-           "tracs_write_distance_csv", "tracs_float_repr", "tracs_pairsnp_packed", "tracs_encode_packed", "tracs_site_shard_finish", "tracs_tc_peak"]
+           "tracs_write_distance_csv", "tracs_float_repr", "tracs_pairsnp_packed", "tracs_encode_packed", "tracs_site_shard_finish", "tracs_tc_peak", "tracs_site_shard_select", "tracs_site_shard_emit",
+           "tracs_host_register", "tracs_host_unregister"]
 
 _lib = None
 
@@ -72,6 +73,11 @@ def lib():
         L.tracs_encode_packed.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
         L.tracs_site_shard_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Opts),
                                               C.POINTER(Edges)]
+        L.tracs_site_shard_select.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Opts),
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.tracs_site_shard_emit.argtypes = [C.c_void_p, C.POINTER(Edges), C.c_size_t, C.POINTER(C.c_int)]
+        L.tracs_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.tracs_host_unregister.argtypes = [C.c_void_p]
         L.tracs_edges_free.argtypes = [C.POINTER(Edges)]
         L.tracs_edges_free.restype = None
         L.tracs_trans_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
@@ -147,6 +153,7 @@ def take_edges(e, as_lists=False, names=True, copy=True):
     """tracs_edges_t -> EdgeTable of numpy arrays (or Python lists). copy=True copies and frees the
     struct at once; copy=False wraps the library's buffers without copying."""
     n = e.n_edges
+    e_has_rows = bool(e.rows) or n == 0
 
     def arr(p, dt):
         if not p:
@@ -165,6 +172,8 @@ def take_edges(e, as_lists=False, names=True, copy=True):
         lib().tracs_edges_free(C.byref(e))
     else:
         out._owner = _EdgeOwner(e)
+    if out["filt"] is None and e_has_rows:
+        out["filt"] = np.zeros(n, np.uint64)   # filter off: the reference returns a vector of zeros (src/pairsnp.hpp:452)
     if as_lists:
         for k in ("rows", "cols", "dist", "filt", "ncomp"):
             out[k] = out[k].tolist()

@@ -42,20 +42,39 @@ __global__ void k_finish_gather(const uint32_t *__restrict__ idx, const uint64_t
 }
 
 // Candidate vectors (device; keys ascending, d = full-length distance, union = |N_i u N_j| or null) -> edge columns on
-// the host: threshold, compared sites, fused likelihood. Shared by the single-GPU filter-and-refine path and by
-// the last step of the site-sharded sweep.
-static void finish_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
-                              uint64_t L_total, const tracs_opts_t &o, TransLut *lut_in, HostEdges &out, cudaStream_t st) {
+// the host, in two phases: SELECT (threshold, compared sites; leaves the selected columns on the device and returns the
+// count) and EMIT (fused likelihood + copies into host columns given by the caller). finish_candidates() runs both into
+// library-owned page-locked columns; the site-sharded sweep at N > 1 runs them apart, with an all-gather of the counts
+// in between, so that every rank writes its share of the edge table over its own PCIe link (tracs_site_shard_select /
+// _emit).
+struct Selection {
+  uint64_t E = 0, n = 0;
+  bool want_n = false;
+  tracs_opts_t o;
+  std::vector<int32_t> days;  // copy: the caller's array need not outlive select()
+  DevBuf<uint64_t> keys_o, rows, cols, dist, nc;
+  DevBuf<uint32_t> d_o;
+};
+struct HostColumns {  // destination of emit(): caller-owned host arrays (page-locked / registered), element offset applied
+  uint64_t *rows, *cols, *dist, *ncomp;
+  double *p0_log, *eK, *datediff;
+};
+
+static void select_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
+                              uint64_t L_total, const tracs_opts_t &o, Selection &sel, cudaStream_t st) {
   tracs_stats_t &S = g_stats;
+  sel.E = 0;
+  sel.n = n;
+  sel.o = o;
+  sel.want_n = dev_union != nullptr;
+  if (o.days) {
+    sel.days.assign(o.days, o.days + n);
+    sel.o.days = sel.days.data();
+  }
   if (n_keys == 0) return;
   if (n_keys >= (1ull << 32)) throw std::runtime_error("too many candidates");
   Timer T(st);
   T.start();
-  TransLut lut_own;
-  bool fuse = lut_in != nullptr;
-  if (!fuse) fuse = lut_own.setup(o, n, (uint64_t)std::max<int64_t>(o.dist, 0) + 1, st);
-  TransLut &lut = lut_in ? *lut_in : lut_own;
-  const bool want_n = dev_union != nullptr;
   DevBuf<uint8_t> flags(n_keys);
   DevBuf<uint32_t> idx(n_keys);
   DevBuf<uint64_t> n_sel(1);
@@ -66,10 +85,10 @@ static void finish_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, c
   DevBuf<uint8_t> tmp(tb);
   cub::DeviceSelect::Flagged(tmp.p, tb, cnt_it, flags.p, idx.p, n_sel.p, (int64_t)n_keys, st);
   // columns are sized by the candidate count (an upper bound): no host round trip before the gather
-  DevBuf<uint64_t> keys_o(n_keys), d_rows(n_keys), d_cols(n_keys), d_dist(n_keys), d_nc(n_keys);
-  DevBuf<uint32_t> d_o(n_keys);
-  k_finish_gather<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(idx.p, n_sel.p, dev_keys, dev_d, dev_union, L_total, keys_o.p, d_o.p,
-                                                                   d_rows.p, d_cols.p, d_dist.p, d_nc.p);
+  sel.keys_o.alloc(n_keys); sel.rows.alloc(n_keys); sel.cols.alloc(n_keys); sel.dist.alloc(n_keys); sel.nc.alloc(n_keys);
+  sel.d_o.alloc(n_keys);
+  k_finish_gather<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(idx.p, n_sel.p, dev_keys, dev_d, dev_union, L_total, sel.keys_o.p,
+                                                                   sel.d_o.p, sel.rows.p, sel.cols.p, sel.dist.p, sel.nc.p);
   S.kernel_launches += 4;
   TRACS_CK(cudaGetLastError());
   uint64_t E = 0;
@@ -77,31 +96,59 @@ static void finish_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, c
   TRACS_CK(cudaStreamSynchronize(st));
   S.ms_sort += T.stop();
   S.n_edges += E;
-  if (E == 0) return;
-  const size_t old = out.rows.size();
-  out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E);
-  if (want_n) out.ncomp.resize(old + E);
-  TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, d_rows.p, E * 8, cudaMemcpyDeviceToHost, st));
-  TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, d_cols.p, E * 8, cudaMemcpyDeviceToHost, st));
-  TRACS_CK(cudaMemcpyAsync(out.dist.data() + old, d_dist.p, E * 8, cudaMemcpyDeviceToHost, st));
-  if (want_n) TRACS_CK(cudaMemcpyAsync(out.ncomp.data() + old, d_nc.p, E * 8, cudaMemcpyDeviceToHost, st));
-  S.d2h_bytes += E * (want_n ? 32 : 24);
+  sel.E = E;
+}
+
+// returns whether the likelihood columns were written
+static bool emit_selection(Selection &sel, const HostColumns &dst, TransLut *lut_in, cudaStream_t st) {
+  tracs_stats_t &S = g_stats;
+  const uint64_t E = sel.E;
+  if (E == 0) return false;
+  Timer T(st);
+  TRACS_CK(cudaMemcpyAsync(dst.rows, sel.rows.p, E * 8, cudaMemcpyDeviceToHost, st));
+  TRACS_CK(cudaMemcpyAsync(dst.cols, sel.cols.p, E * 8, cudaMemcpyDeviceToHost, st));
+  TRACS_CK(cudaMemcpyAsync(dst.dist, sel.dist.p, E * 8, cudaMemcpyDeviceToHost, st));
+  if (sel.want_n) TRACS_CK(cudaMemcpyAsync(dst.ncomp, sel.nc.p, E * 8, cudaMemcpyDeviceToHost, st));
+  S.d2h_bytes += E * (sel.want_n ? 32 : 24);
+  TransLut lut_own;
+  bool fuse = lut_in != nullptr;
+  if (!fuse) fuse = lut_own.setup(sel.o, sel.n, (uint64_t)std::max<int64_t>(sel.o.dist, 0) + 1, st);
+  TransLut &lut = lut_in ? *lut_in : lut_own;
   DevBuf<double> d_p0, d_eK, d_dt;
   if (fuse) {
     T.start();
-    out.has_trans = true;
     d_p0.alloc(E); d_eK.alloc(E); d_dt.alloc(E);
-    out.p0_log.resize(old + E); out.eK.resize(old + E); out.datediff.resize(old + E);
-    lut.apply(keys_o.p, d_o.p, E, d_p0.p, d_eK.p, d_dt.p, st);
+    lut.apply(sel.keys_o.p, sel.d_o.p, E, d_p0.p, d_eK.p, d_dt.p, st);
     S.ms_trans += T.stop();
-    TRACS_CK(cudaMemcpyAsync(out.p0_log.data() + old, d_p0.p, E * 8, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaMemcpyAsync(out.eK.data() + old, d_eK.p, E * 8, cudaMemcpyDeviceToHost, st));
-    TRACS_CK(cudaMemcpyAsync(out.datediff.data() + old, d_dt.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(dst.p0_log, d_p0.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(dst.eK, d_eK.p, E * 8, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(dst.datediff, d_dt.p, E * 8, cudaMemcpyDeviceToHost, st));
     S.d2h_bytes += E * 24;
   }
   T.start();
   TRACS_CK(cudaStreamSynchronize(st));
   S.ms_d2h += T.stop();
+  return fuse;
+}
+
+static void finish_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
+                              uint64_t L_total, const tracs_opts_t &o, TransLut *lut_in, HostEdges &out, cudaStream_t st) {
+  Selection sel;
+  select_candidates(dev_keys, dev_d, dev_union, n_keys, n, L_total, o, sel, st);
+  const uint64_t E = sel.E;
+  if (E == 0) return;
+  const bool fuse = lut_in != nullptr || (o.want_trans && o.days && o.dist >= 0);
+  const size_t old = out.rows.size();
+  out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E);
+  if (sel.want_n) out.ncomp.resize(old + E);
+  if (fuse) { out.p0_log.resize(old + E); out.eK.resize(old + E); out.datediff.resize(old + E); }
+  HostColumns dst{out.rows.data() + old, out.cols.data() + old, out.dist.data() + old, sel.want_n ? out.ncomp.data() + old : nullptr,
+                  fuse ? out.p0_log.data() + old : nullptr, fuse ? out.eK.data() + old : nullptr, fuse ? out.datediff.data() + old : nullptr};
+  if (emit_selection(sel, dst, lut_in, st)) {
+    out.has_trans = true;
+  } else if (fuse) {  // table too large for the device-side path: finish_edges() takes the unique-key route
+    out.p0_log.resize(old); out.eK.resize(old); out.datediff.resize(old);
+  }
 }
 
 void site_shard_finish_device(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
@@ -230,6 +277,40 @@ int tracs_site_shard_partials(void *handle, const uint64_t *dev_keys, size_t n_k
     T.start();
     eval_pairs(g, dev_keys, n_keys, dev_d, dev_union, 0);
     g_stats.ms_refine += T.stop();
+  });
+}
+
+int tracs_site_shard_select(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, size_t n_keys, size_t n_samples,
+                            size_t L_total, const tracs_opts_t *opts, void **selection, size_t *n_selected) {
+  *selection = nullptr;
+  *n_selected = 0;
+  memset(&g_stats, 0, sizeof g_stats);
+  return guarded([&] {
+    require_device();
+    if (!opts) throw std::runtime_error("site shard: options required");
+    std::unique_ptr<Selection> sel(new Selection());
+    tracs_opts_t o = *opts;
+    o.filter = 0;
+    select_candidates(dev_keys, dev_d, dev_union, n_keys, n_samples, L_total, o, *sel, 0);
+    *n_selected = sel->E;
+    *selection = sel.release();
+  });
+}
+
+int tracs_site_shard_emit(void *selection, const tracs_edges_t *dst, size_t at, int *has_trans) {
+  std::unique_ptr<Selection> sel((Selection *)selection);
+  if (has_trans) *has_trans = 0;
+  return guarded([&] {
+    if (!sel) throw std::runtime_error("site shard: null selection");
+    if (!dst || !dst->rows || !dst->cols || !dst->dist) throw std::runtime_error("site shard: destination columns required");
+    const bool fuse = sel->o.want_trans && sel->o.days && dst->p0_log && dst->eK && dst->datediff;
+    if (!fuse) sel->o.want_trans = 0;
+    if (sel->want_n && !dst->ncomp) throw std::runtime_error("site shard: destination for the compared-sites column required");
+    HostColumns hc{dst->rows + at, dst->cols + at, dst->dist + at, dst->ncomp ? dst->ncomp + at : nullptr,
+                   fuse ? dst->p0_log + at : nullptr, fuse ? dst->eK + at : nullptr, fuse ? dst->datediff + at : nullptr};
+    const bool wrote = emit_selection(*sel, hc, nullptr, 0);
+    if (fuse && sel->E && !wrote) throw std::runtime_error("site shard: the (distance, day) table is too large for the fused likelihood");
+    if (has_trans) *has_trans = wrote ? 1 : 0;
   });
 }
 

@@ -6,13 +6,17 @@ d(i,j) and |N_i u N_j| are sums over disjoint site ranges (src/pairsnp.hpp:398-4
   gather    candidate pair lists are all-gathered                        (NCCL all-gather, O(candidates))
   partials  every rank evaluates its slab's share of d and |N u N| for all candidates
   reduce    the two integer vectors are summed over ranks               (NCCL all-reduce)
-  finish    rank 0, native (tracs_site_shard_finish): d <= dist, compared sites = L_total - union, fused
-            transmission likelihood, columns to page-locked host memory
+  finish    every rank, native, on its slice of the candidates (tracs_site_shard_select / _emit): d <= dist, compared
+            sites = L_total - union, fused transmission likelihood; each GPU copies its edges into ONE shared,
+            page-locked host table over its own PCIe link (SharedEdgeTable); world 1: tracs_site_shard_finish
 No bit-plane crosses NVLink. Results equal the single-GPU sweep of the whole alignment.
 
 The collective plumbing is torch.distributed; the three compute steps go through a small backend object so that
 the exchange logic runs under gloo on CPU in tests (tests/test_multi_gloo.py) with the oracle standing in."""
 import ctypes as C
+import itertools
+import mmap
+import os
 
 import numpy as np
 
@@ -67,10 +71,93 @@ class LibBackend:
                                                       int(keys.numel()), self.n, L_total, C.byref(o), C.byref(e)))
         return _lib.take_edges(e, names=False, copy=False), _lib.last_stats()
 
+    def select(self, keys, d, u, L_total, dist, days, lamb, beta, threshold_Ek):
+        """First half of the sharded finish on a slice of the candidates -> (selection handle, edge count, stats)."""
+        o, keep = api.make_opts(dist=dist, days=days, lamb=lamb, beta=beta, threshold_Ek=threshold_Ek)
+        sel, cnt = C.c_void_p(), C.c_size_t(0)
+        _lib.check(_lib.lib().tracs_site_shard_select(C.c_void_p(keys.data_ptr()), C.c_void_p(d.data_ptr()), C.c_void_p(u.data_ptr()),
+                                                      int(keys.numel()), self.n, L_total, C.byref(o), C.byref(sel), C.byref(cnt)))
+        return sel, cnt.value, _lib.last_stats()
+
+    def emit(self, sel, table, at):
+        """Second half: likelihood columns + device -> host copies into the shared table at row `at`."""
+        e = table.as_edges()
+        ht = C.c_int(0)
+        _lib.check(_lib.lib().tracs_site_shard_emit(sel, C.byref(e), int(at), C.byref(ht)))
+        return bool(ht.value), _lib.last_stats()
+
     def close(self):
         if self.h is not None:
             _lib.lib().tracs_site_shard_close(self.h)
             self.h = None
+
+
+class SharedEdgeTable:
+    """The edge table of a multi-process run: seven 8-byte columns in ONE shared-memory segment that every rank maps
+    and page-locks, so that each GPU copies its slice of the edges straight into place over its own PCIe link and
+    rank 0 reads the whole table without a gather through one GPU. Rank 0 creates the segment, the name is broadcast,
+    and the file is unlinked as soon as everybody has mapped it."""
+    COLS = (("rows", np.uint64), ("cols", np.uint64), ("dist", np.uint64), ("ncomp", np.uint64), ("p0_log", np.float64),
+            ("eK", np.float64), ("datediff", np.float64))
+    _serial = itertools.count()
+
+    def __init__(self, dist_mod, rank, world, capacity, page_lock=True):
+        self.capacity = int(capacity)
+        self.nbytes = 8 * len(self.COLS) * self.capacity
+        name = [None]
+        if rank == 0:
+            name[0] = "/dev/shm/tracs_edges_%d_%d" % (os.getpid(), next(self._serial))
+            fd = os.open(name[0], os.O_CREAT | os.O_RDWR | os.O_EXCL, 0o600)
+            os.ftruncate(fd, self.nbytes)
+        if world > 1:
+            dist_mod.broadcast_object_list(name, src=0)
+        if rank != 0:
+            fd = os.open(name[0], os.O_RDWR)
+        self.mm = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        self.buf = np.frombuffer(self.mm, dtype=np.uint8)
+        self.locked = False
+        if page_lock:
+            _lib.check(_lib.lib().tracs_host_register(self.buf.ctypes.data, self.nbytes))
+            self.locked = True
+        if world > 1:
+            dist_mod.barrier()
+        if rank == 0:
+            os.unlink(name[0])
+        self.views = {}
+        for k, (c, dt) in enumerate(self.COLS):
+            self.views[c] = self.buf[k * 8 * self.capacity:(k + 1) * 8 * self.capacity].view(dt)
+
+    def as_edges(self):
+        """tracs_edges_t whose column pointers are the table's columns (destination of tracs_site_shard_emit)."""
+        e = _lib.Edges()
+        for c, dt in self.COLS:
+            ct = C.c_uint64 if dt is np.uint64 else C.c_double
+            setattr(e, c, C.cast(self.views[c].ctypes.data, C.POINTER(ct)))
+        return e
+
+    def close(self):
+        if self.locked:
+            _lib.lib().tracs_host_unregister(self.buf.ctypes.data)
+            self.locked = False
+        self.views = {}
+        self.buf = None
+        try:
+            self.mm.close()
+        except BufferError:
+            pass
+
+
+_TABLE = None  # this process's shared edge table (kept across sweeps, grown collectively when too small)
+
+
+def _shared_table(dist_mod, rank, world, need, page_lock):
+    global _TABLE
+    if _TABLE is None or _TABLE.capacity < need:     # `need` is the same on every rank: a collective decision
+        if _TABLE is not None:
+            _TABLE.close()
+        _TABLE = SharedEdgeTable(dist_mod, rank, world, int(need * 1.25) + 1024, page_lock=page_lock)
+    return _TABLE
 
 
 def exchange_candidates(torch, dist_mod, device, world, mine):
@@ -121,10 +208,32 @@ def sweep(torch, dist_mod, device, rank, world, slab_ptr, n, L_slab, pitch, L_to
         stats = dict(st_open)
         stats.update(st_part)   # the library's counters run on from open() through partials()
         stats["n_candidates_all"] = E
-        if profile:
-            stats["phases_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks, marks[1:])}
-        if rank != 0:
-            return None, stats
+        if world > 1:
+            # sharded finish: every rank thresholds a contiguous slice of the (identical) summed vectors, the counts are
+            # all-gathered, and each rank copies its edges into the shared host table at its offset
+            lo, hi = E * rank // world, E * (rank + 1) // world
+            sel, cnt, st_sel = be.select(keys[lo:hi], both[0][lo:hi], both[1][lo:hi], L_total, dist, days, lamb, beta, threshold_Ek)
+            cnts = torch.zeros(world, dtype=torch.int64, device=device)
+            dist_mod.all_gather_into_tensor(cnts, torch.tensor([cnt], dtype=torch.int64, device=device))
+            cs = cnts.tolist()
+            total = int(sum(cs))
+            table = _shared_table(dist_mod, rank, world, total, page_lock=(device.type == "cuda"))
+            has_trans, st_emit = be.emit(sel, table, int(sum(cs[:rank])))
+            dist_mod.barrier()      # every slice has landed in the table
+            mark("finish")
+            for k in ("ms_trans", "ms_d2h", "d2h_bytes"):
+                stats[k] = st_emit.get(k, 0)
+            stats["kernel_launches"] = stats.get("kernel_launches", 0) + st_sel.get("kernel_launches", 0) + st_emit.get("kernel_launches", 0)
+            stats["ms_finish"] = st_sel.get("ms_sort", 0.0)
+            stats["n_edges"] = total
+            if profile:
+                stats["phases_ms"] = {b[0]: 1e3 * (b[1] - a[1]) for a, b in zip(marks, marks[1:])}
+            if rank != 0:
+                return None, stats
+            res = {c: table.views[c][:total] for c, _ in SharedEdgeTable.COLS if has_trans or c not in ("p0_log", "eK", "datediff")}
+            for c in ("p0_log", "eK", "datediff"):
+                res.setdefault(c, None)
+            return res, stats     # views of the shared table: valid until the next sweep
         res, st_fin = be.finish(keys, both[0], both[1], L_total, dist, days, lamb, beta, threshold_Ek)
         mark("finish")
         if profile:
