@@ -25,3 +25,14 @@ for V in native v3; do
 done
 wait
 ls "$OUT"/native/TRACS$EXT "$OUT"/v3/TRACS$EXT
+# The reference's Python callers of the native module and its own tests of the hot path, staged UNCHANGED under the
+# git-ignored oracle/_ref/py/ so that the GPU box (which has no /root/reference) can run them on top of the CUDA
+# drop-in (tests/test_gpu_reference_callers.py). pyfastx is imported by tracs/utils.py:8 at module top and never used
+# on this path: an empty stub module stands in for it.
+PY="$OUT/py"
+rm -rf "$PY"
+mkdir -p "$PY/tracs" "$PY/ref_tests"
+for f in __init__ distance transcluster cluster utils threshold; do cp "$REF/tracs/$f.py" "$PY/tracs/$f.py"; done
+for f in conftest test_llk test_pairsnp test_trans_distance; do cp "$REF/tests/$f.py" "$PY/ref_tests/$f.py"; done
+printf '"""stub: tracs/utils.py imports pyfastx at module top; nothing on the distance / cluster path uses it"""\n' > "$PY/pyfastx.py"
+ls "$PY/tracs" "$PY/ref_tests"

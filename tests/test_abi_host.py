@@ -274,3 +274,31 @@ def test_native_csv_writer_layout(tmp_path):
     _lib.check(L.tracs_write_distance_csv(out.encode(), 1, C.byref(e), names, 3, b"k2", 0, 0, 0, 0.0, C.byref(w)))
     lines = open(out).read().splitlines()
     assert w.value == 3 and lines[3] == "seq1,seq2,NA,0,NA,NA,0,9,k2"             # no metadata: NA columns, filtered column = 0
+
+
+def test_compiled_pybind_module_surface(tmp_path):
+    """The compiled `TRACS` extension (tracs_b200/dropin_native/, pybind11 over the C ABI; INTEGRATION.md option B):
+    same four names and keywords as src/python_bindings.cpp:12-25, host-side entries work without a GPU, device
+    entries fail loudly; the reference's own tests/test_llk.py passes on it when staged."""
+    import subprocess, sys
+    from tracs_b200 import build
+    path = build.build_pybind()
+    d = os.path.dirname(path)
+    code = ("import TRACS, inspect, numpy as np\n"
+            "from scipy.special import gammaln\n"
+            "assert TRACS.__file__.endswith('.so') and TRACS.__doc__ == 'Meta Transmission Clustering'\n"
+            "assert sorted(n for n in dir(TRACS) if not n.startswith('_')) == ['calculate_posteriors', 'lprob_k_given_N', 'pairsnp', 'trans_dist']\n"
+            "r = TRACS.lprob_k_given_N(N=7, k=4, delta=0.16963, lamb=3, beta=52, lgamma=gammaln(range(20)))\n"
+            "assert abs(r[0] + 17.9565184209608) < 1e-6 and abs(r[1] - 12.0861694243766) < 1e-6\n"
+            "try:\n    TRACS.lprob_k_given_N(7, 4, 0.1, 3, 52, [0.0] * 5)\n    raise SystemExit(2)\nexcept IndexError:\n    pass\n"
+            "p = TRACS.calculate_posteriors(counts=np.array([[1., 2.], [0., 0.]]), alphas=[0.5, 0.2], keep=True, threshold=0.05)\n"
+            "assert p.shape == (2, 2) and p.dtype == np.float64\n"
+            "try:\n    TRACS.pairsnp(fasta=['a', 'b', 'c'], n_threads=1, dist=1, filter=False)\n    raise SystemExit(3)\n"
+            "except RuntimeError as e:\n    assert 'Invalid number of fasta files' in str(e)\n")
+    env = dict(os.environ, PYTHONPATH=d)
+    subprocess.check_call([sys.executable, "-c", code], env=env, cwd=str(tmp_path))
+    t = os.path.join(ROOT, "oracle", "_ref", "py", "ref_tests")
+    if os.path.exists(os.path.join(t, "test_llk.py")):
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", t, os.path.join(t, "test_llk.py")],
+                           env=env, cwd=str(tmp_path), capture_output=True, text=True)
+        assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout + r.stderr

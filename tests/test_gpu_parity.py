@@ -393,3 +393,30 @@ def test_tensor_core_sweep_modes(oracle_mod):
     order = np.argsort(key, kind="stable")
     for k in ("rows", "cols", "dist", "ncomp"):
         assert np.concatenate([p[k] for p in parts])[order].tolist() == one[k].tolist()
+
+
+def test_filter_decisions_match_incomplete_beta_cdf():
+    """k_filter_recomb sums the binomial pmf term by term; Boost (what the reference links) evaluates the regularised
+    incomplete beta function. On near-threshold SNP layouts the kernel's filt must equal the windowing restated in
+    Python with scipy.stats.binom (an incomplete-beta implementation) -- see tests/test_filter_pin.py for the margins."""
+    from scipy import stats
+    from oracle import binom_check as bc
+    rng = np.random.default_rng(11)
+    L, n = 200_000, 161
+    base = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L)]
+    s = np.repeat(base[None, :], n, axis=0)
+    layouts = [None]
+    for k in range(1, n):
+        snp = set(rng.choice(L, size=int(rng.integers(3, 60)), replace=False).tolist())
+        start, width = int(rng.integers(1000, L - 6000)), int(rng.integers(20, 5000))
+        snp |= set((start + rng.choice(width, size=min(int(rng.integers(2, 12)), width), replace=False)).tolist())
+        snp = np.array(sorted(snp))
+        s[k, snp] = np.where(base[snp] == ord("A"), ord("C"), ord("A"))
+        layouts.append(snp.tolist())
+    res = tracs_b200.pairsnp_matrix(s, dist=IMAX, filter=True, want_ncomp=False)
+    first = {int(c): (int(d), int(f)) for r, c, d, f in zip(res["rows"], res["cols"], res["dist"], res["filt"]) if r == 0}
+    cdf = lambda nn, p, k: 1.0 if k >= nn else float(stats.binom.cdf(k, nn, p))
+    for k in range(1, n):
+        d, f = first[k]
+        assert d == len(layouts[k])
+        assert f == bc.filtered_distance(layouts[k], L, cdf)[0], k

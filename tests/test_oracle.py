@@ -131,3 +131,13 @@ def test_live_reference(oracle_mod, ref_mod, tmp_path):
     z = (~pos) & np.isfinite(np.array(a[1]))
     assert z.sum() > 0 and np.allclose(np.array(a[1])[z], b[1][z], rtol=1e-6)
     assert np.allclose(b[1][~pos], (N[~pos] + 1) * 73.0 / 29.903, rtol=1e-9)
+
+
+def test_reconstructed_reference_fixture(ref_mod):
+    """tests/golden/ref_fixture/ambig.aln stands in for the absent fixture of the reference's tests/test_pairsnp.py:5-9:
+    on the UNMODIFIED reference module it gives exactly the vectors that test asserts."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fixture", "ambig.aln")
+    r = ref_mod.pairsnp(fasta=[p], n_threads=1, dist=10, filter=False)
+    assert list(r[0]) == [0, 0, 0, 0, 1, 1, 1, 2, 2, 3]
+    assert list(r[1]) == [1, 2, 3, 4, 2, 3, 4, 3, 4, 4]
+    assert list(r[2]) == [0, 2, 1, 1, 2, 2, 2, 3, 3, 0]

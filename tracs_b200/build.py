@@ -23,7 +23,7 @@ def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "tracs_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "pybind_module.cpp"] + [os.path.join(HERE, "..", "include", "tracs_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -54,5 +54,28 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+def pybind_path():
+    import sysconfig
+    return os.path.join(HERE, "dropin_native", "TRACS" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pybind(force=False):
+    """The compiled `TRACS` extension module (pybind11) over the C ABI: tracs_b200/dropin_native/TRACS<ext>.so, linked
+    against libtracs_b200.so next door (rpath $ORIGIN/..)."""
+    import sysconfig
+    out = pybind_path()
+    src = os.path.join(CSRC, "pybind_module.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "tracs_b200.h"), LIB]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps if os.path.exists(d)):
+        return out
+    import pybind11
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-fvisibility=hidden", "-I" + pybind11.get_include(),
+           "-I" + sysconfig.get_paths()["include"], src, "-o", out, "-L" + HERE, "-ltracs_b200", "-Wl,-rpath,$ORIGIN/.."]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build_lib(force=True, verbose="-v" in sys.argv))
+    print(build_pybind(force=True))
