@@ -178,6 +178,7 @@ def test_fasta_loader_threads_equal_sequential(tmp_path, monkeypatch):
     # the multi-threaded reader of plain files must be indistinguishable from the sequential state machine:
     # same names, order, bases -- and the same error -- also where it has to hand the file back
     monkeypatch.setenv("TRACS_FASTA_PAR_MIN", "0")
+    monkeypatch.setenv("TRACS_FASTA_SINK_CHECK", "1")   # the rows streamed to a sink while parsing == the finished matrix
     cases = {
         "plain": b">a desc here\nACGT\nAC\n>b\nAC-NNT\n>c\nACGTAC\n",
         "crlf": b">a\tx\r\nAC GT\r\n\r\nAC\r\n>b\r\nACGTAC\r\n>c x\r\nACGTAC",
@@ -211,6 +212,13 @@ def test_fasta_loader_threads_equal_sequential(tmp_path, monkeypatch):
         synth.write_fasta(p, s, width=width, descriptions=True)
         a, names = tracs_b200.read_fasta(p, n_threads=8)
         assert names == ["s%d" % i for i in range(64)] and np.array_equal(a, s)
+    # many ~32 MB sink chunks: 600 records x 200 kb through the parallel reader, and gzip through the sequential one
+    s = synth.generate(600, 200_000, p_var=0.01, seed=10)
+    for nm in ("chunks.fa", "chunks.fa.gz"):
+        p = str(tmp_path / nm)
+        synth.write_fasta(p, s if nm.endswith(".fa") else s[:120])
+        a, names = tracs_b200.read_fasta(p, n_threads=8)
+        assert np.array_equal(a, s[:len(a)]) and len(a) == (600 if nm.endswith(".fa") else 120)
 
 
 def test_shard_dealing_covers_and_balances():

@@ -40,6 +40,9 @@ def test_loader_matches_oracle_reader(oracle_mod, tmp_path_factory, data, gz):
     p = str(d / ("x.fa.gz" if gz else "x.fa"))
     with (gzip.open(p, "wb") if gz else open(p, "wb")) as f:
         f.write(text.encode())
+    # TRACS_FASTA_SINK_CHECK: the reader also feeds a row sink while parsing (what the FASTA entry point streams to the
+    # device) and raises if those rows are not exactly the finished matrix, in order
+    os.environ["TRACS_FASTA_SINK_CHECK"] = "1"
     a, names = tracs_b200.read_fasta(p)
     exp = oracle_mod.pairsnp([p], dist=2147483647)
     assert names == exp[3]
@@ -50,6 +53,7 @@ def test_loader_matches_oracle_reader(oracle_mod, tmp_path_factory, data, gz):
         a4, names4 = tracs_b200.read_fasta(p, n_threads=4)
     finally:
         del os.environ["TRACS_FASTA_PAR_MIN"]
+        del os.environ["TRACS_FASTA_SINK_CHECK"]
     assert names4 == names and a4.shape == a.shape and np.array_equal(a4, a)
     if n >= 2 and L > 0:
         got = oracle_mod.pairsnp_ascii(a, dist=2147483647)

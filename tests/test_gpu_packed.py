@@ -235,3 +235,37 @@ def test_filter_offsets_beyond_32_bits(oracle_mod):
         i, j = int(res["rows"][e]), int(res["cols"][e])
         r, c, d, f, nn = oracle_mod.pairsnp_ascii(s[[i, j]], dist=IMAX, filter=True)
         assert int(res["dist"][e]) == int(d[0]) and int(res["filt"][e]) == int(f[0]), (e, i, j)
+
+
+def test_fasta_entry_point_streams_rows_to_the_device(oracle_mod, tmp_path, monkeypatch):
+    """tracs_pairsnp(paths): rows go to the device while the reader is still parsing (DeviceRowStreamer). Plain file
+    (parallel reader, record count known), gzip (sequential reader: the packed matrix grows by doubling), two-file
+    mode, tiny staging slots so that many batches are in flight -- all equal to the oracle and to the
+    parse-then-copy path (TRACS_FASTA_STREAM=0)."""
+    s = synth.generate(420, 30_000, p_var=0.05, n_clusters=6, mu=3, p_N=0.02, p_amb=0.03, seed=77, lowercase=0.05, odd_chars=0.01)
+    monkeypatch.setenv("TRACS_STREAM_CHUNK_BYTES", str(64 * 30_016))
+    monkeypatch.setenv("TRACS_FASTA_PAR_MIN", "0")
+    files = {"plain": (str(tmp_path / "a.fa"), dict(width=0)), "wrapped": (str(tmp_path / "b.fa"), dict(width=70, descriptions=True)),
+             "gz": (str(tmp_path / "c.fa.gz"), dict(width=60))}
+    for tag, (p, kw) in files.items():
+        synth.write_fasta(p, s, **kw)
+        exp = oracle_mod.pairsnp([p], n_threads=4, dist=40)
+        got = tracs_b200.pairsnp(fasta=[p], n_threads=8, dist=40, filter=False)
+        st = tracs_b200.last_stats()
+        assert st["h2d_bytes"] == s.size, tag
+        monkeypatch.setenv("TRACS_FASTA_STREAM", "0")
+        ref = tracs_b200.pairsnp(fasta=[p], n_threads=8, dist=40, filter=False)
+        monkeypatch.delenv("TRACS_FASTA_STREAM")
+        for t in range(6):
+            assert got[t] == exp[t] and ref[t] == exp[t], (tag, t)
+    p1, p2 = str(tmp_path / "q.fa"), str(tmp_path / "db.fa.gz")
+    synth.write_fasta(p1, s[:100], names=["q%d" % i for i in range(100)])
+    synth.write_fasta(p2, s[100:], names=["d%d" % i for i in range(320)])
+    got = tracs_b200.pairsnp(fasta=[p1, p2], n_threads=4, dist=40, filter=False)
+    exp = oracle_mod.pairsnp([p1, p2], dist=40)
+    for t in range(6):
+        assert got[t] == exp[t]
+    bad = str(tmp_path / "other_len.fa")
+    synth.write_fasta(bad, s[:5, :1000])
+    with pytest.raises(RuntimeError, match="variable sequence lengths"):
+        tracs_b200.pairsnp(fasta=[p1, bad], n_threads=2, dist=40, filter=False)

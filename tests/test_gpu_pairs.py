@@ -86,3 +86,22 @@ def test_blocks_with_fused_likelihood_and_two_file_ranges(oracle_mod, monkeypatc
         _cmp(got, oracle_mod.pairsnp_ascii(s, i_end=n1, j_start=n1, dist=25, n_threads=4))
     got = tracs_b200.pairsnp_matrix(s, dist=25, want_ncomp=False)
     assert got["rows"].tolist() == r.tolist() and got["dist"].tolist() == d.tolist() and not got["ncomp"].any()
+
+
+@pytest.mark.parametrize("p_N", [0.002, 0.3])
+def test_dense_and_sparse_N_intersections_agree(oracle_mod, monkeypatch, p_N):
+    """|N_i n N_j| of the component blocks: the summary-guided kernel (k_block_n) and the dense AND + POPC contraction
+    over whole N-plane rows (k_block_d<1>, picked automatically for N-rich alignments such as BASELINE configs[3]),
+    each forced on both kinds of data, against the oracle."""
+    s = synth.generate(500, 150_000, p_var=0.08, n_clusters=25, mu=4, p_N=p_N, p_amb=0.02, seed=int(p_N * 1000) + 3, gaps=3)
+    dist = 25 if p_N < 0.1 else 12
+    orc = oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=8)
+    for mode in ("dense", "sparse", None):
+        if mode:
+            monkeypatch.setenv("TRACS_NBLOCKS", mode)
+        else:
+            monkeypatch.delenv("TRACS_NBLOCKS")
+        res = tracs_b200.pairsnp_matrix(s, dist=dist)
+        assert tracs_b200.last_stats()["ms_refine"] > 0
+        _cmp(res, orc)
+    assert len(orc[0]) > 500

@@ -495,6 +495,95 @@ static void stream_host_to_packed(const uint8_t *seqs, size_t n, size_t L, size_
   g_stats.h2d_bytes += (uint64_t)n * L;
 }
 
+// RowSink of the FASTA entry point: rows arrive from the reader while it is still parsing; each batch is copied
+// into a page-locked staging buffer, sent to the device on a copy stream and encoded into the resident packed
+// alignment on the compute stream. Two staging slots: the host memcpy of batch k + 1 overlaps the DMA of batch k,
+// the encode of batch k overlaps both. The packed alignment grows by doubling when the record count is not known
+// up front (gz / sequential reader).
+struct DeviceRowStreamer : RowSink {
+  cudaStream_t st, cp = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  uint8_t *hbuf[2] = {nullptr, nullptr};
+  DevBuf<uint8_t> dbuf[2], nib;
+  uint64_t L = 0, pitch4 = 0, apitch = 0, cap_rows = 0, n_rows = 0, hint_rows = 0;
+  size_t slot_bytes = 0;
+  unsigned turn = 0;
+  explicit DeviceRowStreamer(cudaStream_t s) : st(s) {
+    TRACS_CK(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      TRACS_CK(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+      TRACS_CK(cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming));
+    }
+  }
+  ~DeviceRowStreamer() override {
+    cudaStreamSynchronize(cp);
+    cudaStreamSynchronize(st);
+    for (int b = 0; b < 2; ++b) {
+      if (hbuf[b]) host_pool_free(hbuf[b]);
+      if (ev_copied[b]) cudaEventDestroy(ev_copied[b]);
+      if (ev_free[b]) cudaEventDestroy(ev_free[b]);
+    }
+    if (cp) cudaStreamDestroy(cp);
+  }
+  void expect(uint64_t total_rows, uint64_t) override { hint_rows = std::max(hint_rows, total_rows); }
+  void reset() override {
+    TRACS_CK(cudaStreamSynchronize(cp));
+    TRACS_CK(cudaStreamSynchronize(st));
+    n_rows = 0;
+  }
+  void reserve_rows(uint64_t want) {
+    if (want <= cap_rows) return;
+    uint64_t c = std::max<uint64_t>(std::max(want, hint_rows), cap_rows * 2);
+    DevBuf<uint8_t> bigger(c * pitch4);
+    if (n_rows) {
+      TRACS_CK(cudaStreamSynchronize(cp));
+      TRACS_CK(cudaMemcpyAsync(bigger.p, nib.p, n_rows * pitch4, cudaMemcpyDeviceToDevice, st));
+      TRACS_CK(cudaStreamSynchronize(st));
+    }
+    std::swap(nib.p, bigger.p);
+    std::swap(nib.n, bigger.n);
+    cap_rows = c;
+  }
+  void rows(const uint8_t *p, uint64_t first_row, uint64_t count, uint64_t Lr) override {
+    if (count == 0) return;
+    if (L == 0) {
+      if (Lr == 0) return;
+      L = Lr;
+      pitch4 = std::max<uint64_t>(16, (L + 31) / 32 * 16);
+      apitch = (L + 31) / 32 * 32;
+      const char *env_ch = getenv("TRACS_STREAM_CHUNK_BYTES");
+      slot_bytes = std::max<size_t>(apitch, env_ch ? (size_t)strtoull(env_ch, nullptr, 10) : ((size_t)32 << 20));
+      for (int b = 0; b < 2; ++b) {
+        hbuf[b] = (uint8_t *)host_pool_alloc(slot_bytes);
+        dbuf[b].alloc(slot_bytes);
+      }
+    }
+    if (Lr != L) throw std::runtime_error("Error reading FASTA, variable sequence lengths!");
+    if (first_row != n_rows) throw std::runtime_error("internal error: rows streamed out of order");
+    reserve_rows(first_row + count);
+    const uint64_t R = std::max<uint64_t>(1, slot_bytes / apitch);
+    for (uint64_t r0 = 0; r0 < count; r0 += R) {
+      const uint64_t nr = std::min(R, count - r0);
+      const int b = (int)(turn++ & 1u);
+      if (used[b]) TRACS_CK(cudaEventSynchronize(ev_free[b]));  // the encode that read this slot's device half is done (so is its DMA)
+      for (uint64_t r = 0; r < nr; ++r) memcpy(hbuf[b] + r * L, p + (r0 + r) * L, L);
+      TRACS_CK(cudaMemcpy2DAsync(dbuf[b].p, apitch, hbuf[b], L, L, nr, cudaMemcpyHostToDevice, cp));
+      TRACS_CK(cudaEventRecord(ev_copied[b], cp));
+      TRACS_CK(cudaStreamWaitEvent(st, ev_copied[b], 0));
+      encode_rows_device(dbuf[b].p, nr, L, apitch, nib.p + (first_row + r0) * pitch4, pitch4, st);
+      TRACS_CK(cudaEventRecord(ev_free[b], st));
+      used[b] = true;
+    }
+    n_rows = first_row + count;
+    g_stats.h2d_bytes += count * L;
+  }
+  void finish() {
+    TRACS_CK(cudaStreamSynchronize(cp));
+    TRACS_CK(cudaStreamSynchronize(st));
+  }
+};
+
 int tracs_encode_packed(const uint8_t *dev_ascii, size_t rows, size_t L, size_t pitch, uint8_t *dev_nib, size_t pitch_bytes) {
   return guarded([&] {
     require_device();
@@ -580,30 +669,48 @@ int tracs_pairsnp(const char *const *paths, int n_paths, int n_threads, int32_t 
     // src/pairsnp.hpp:340-343
     if (n_paths < 1 || n_paths > 2) throw std::runtime_error("Invalid number of fasta files!");
     require_device();
+    // The reader hands completed rows to the device while it is still parsing (DeviceRowStreamer): host -> device
+    // copies and the ASCII -> nibble encode overlap the parse; the pair sweep starts on the resident packed alignment
+    // as soon as the last record is in. TRACS_FASTA_STREAM=0: parse everything first, then copy (tests compare).
+    const char *env_stream = getenv("TRACS_FASTA_STREAM");
+    const bool streaming = !(env_stream && !strcmp(env_stream, "0"));
     ByteBuf ascii;
     std::vector<std::string> names;
     uint64_t L = 0, L2 = 0;
-    const uint64_t n1 = read_fasta(paths[0], n_threads, ascii, names, L);
+    std::unique_ptr<DeviceRowStreamer> ds(streaming ? new DeviceRowStreamer(0) : nullptr);
+    const uint64_t n1 = read_fasta(paths[0], n_threads, ascii, names, L, ds.get(), 0);
     uint64_t n = n1;
     tracs_opts_t o;
     memset(&o, 0, sizeof o);
     o.dist = dist; o.filter = filter; o.want_ncomp = 1; o.i_end = n1; o.j_start = 0;
     if (n_paths == 2) {
       L2 = L;
-      const uint64_t n2 = read_fasta(paths[1], n_threads, ascii, names, L2);
-      // the reference does not cross-check the files (bitsets of unequal size: undefined); refuse
+      // the reference does not cross-check the files (bitsets of unequal size: undefined); refuse (the streamer
+      // raises the same error when the second file's rows have another length)
+      const uint64_t n2 = read_fasta(paths[1], n_threads, ascii, names, L2, (n1 > 0 && L > 0) ? ds.get() : nullptr, n1);
       if (n2 > 0 && n1 > 0 && L2 != L) throw std::runtime_error("Error reading FASTA, variable sequence lengths!");
       if (n1 == 0) L = L2;
       n += n2;
       o.j_start = n1;
     }
     tracs_edges_t tmp;
-    const int rc = (n1 == 0 || o.j_start >= n) ? 0 : tracs_pairsnp_host(ascii.data(), n, L, L, &o, &tmp);
+    int rc = 0;
     if (n1 == 0 || o.j_start >= n) {
       memset(&tmp, 0, sizeof tmp);
       tmp.rows = (uint64_t *)calloc(1, 8); tmp.cols = (uint64_t *)calloc(1, 8); tmp.dist = (uint64_t *)calloc(1, 8);
       tmp.filt = nullptr; tmp.ncomp = (uint64_t *)calloc(1, 8);
       tmp.seq_length = L;
+    } else if (ds && L > 0 && ds->n_rows == n) {
+      ds->finish();
+      memset(&tmp, 0, sizeof tmp);
+      tracs_opts_t on = normalise(&o, n);
+      on.packed_input = 1;
+      HostEdges he;
+      sweep_device(ds->nib.p, n, L, ds->pitch4, on, he, 0);
+      finish_edges(he, on, n, L, &tmp, 0);
+    } else {
+      ds.reset();
+      rc = tracs_pairsnp_host(ascii.data(), n, L, L, &o, &tmp);
     }
     if (rc) throw std::runtime_error(g_err);
     *out = tmp;
@@ -619,7 +726,27 @@ int tracs_read_fasta(const char *path, int n_threads, uint8_t **seqs, size_t *n,
     ByteBuf ascii;
     std::vector<std::string> nm;
     uint64_t len = 0;
-    const uint64_t cnt = read_fasta(path, n_threads, ascii, nm, len);
+    // TRACS_FASTA_SINK_CHECK=1 (tests): read with a collecting RowSink as well and insist that the rows it was fed while
+    // the reader was parsing are exactly the rows of the finished matrix, in order
+    struct CollectSink : RowSink {
+      std::vector<uint8_t> buf;
+      uint64_t L = 0, n = 0;
+      bool bad = false;
+      void expect(uint64_t, uint64_t) override {}
+      void rows(const uint8_t *p, uint64_t first, uint64_t count, uint64_t Lr) override {
+        if (L == 0) L = Lr;
+        if (Lr != L || first != n) bad = true;
+        buf.insert(buf.end(), p, p + count * Lr);
+        n += count;
+      }
+      void reset() override { buf.clear(); n = 0; L = 0; }
+    } sink;
+    const char *chk = getenv("TRACS_FASTA_SINK_CHECK");
+    const bool check = chk && !strcmp(chk, "1");
+    const uint64_t cnt = read_fasta(path, n_threads, ascii, nm, len, check ? &sink : nullptr, 0);
+    if (check && cnt > 0 && len > 0 &&
+        (sink.bad || sink.n != cnt || sink.L != len || sink.buf.size() != ascii.size() || memcmp(sink.buf.data(), ascii.data(), ascii.size()) != 0))
+      throw std::runtime_error("internal error: rows streamed by the reader differ from the parsed matrix");
     *seqs = ascii.release();
     *names = (char **)malloc(std::max<size_t>(1, nm.size()) * sizeof(char *));
     for (size_t i = 0; i < nm.size(); ++i) (*names)[i] = strdup(nm[i].c_str());

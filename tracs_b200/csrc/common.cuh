@@ -173,8 +173,20 @@ struct Alignment {
   std::vector<std::string> names;
   uint64_t n = 0, L = 0;
 };
-// appends the records of `path`; returns number of records read; throws std::runtime_error
-uint64_t read_fasta(const char *path, int n_threads, ByteBuf &ascii, std::vector<std::string> &names, uint64_t &L);
+// Consumer of parsed rows while the reader is still parsing (the FASTA entry point streams them to the device):
+// rows() is called from the reader's coordinating thread, in row order, with a pointer to `count` complete rows of
+// `L` bytes each; reset() tells the consumer to forget everything it was given (the parallel reader found out that
+// the file needs the sequential state machine and starts over).
+struct RowSink {
+  virtual void expect(uint64_t total_rows, uint64_t L) = 0;  // optional hint, before the first rows()
+  virtual void rows(const uint8_t *p, uint64_t first_row, uint64_t count, uint64_t L) = 0;
+  virtual void reset() = 0;
+  virtual ~RowSink() {}
+};
+// appends the records of `path`; returns number of records read; throws std::runtime_error. `sink` (optional) is fed
+// the rows as they complete, numbered from `row0`.
+uint64_t read_fasta(const char *path, int n_threads, ByteBuf &ascii, std::vector<std::string> &names, uint64_t &L,
+                    RowSink *sink = nullptr, uint64_t row0 = 0);
 
 // Static multi-GPU partition: row-blocks of 128 samples are dealt boustrophedon
 // (0..w-1, w-1..0, ...) so every shard sweeps (nearly) the same triangle area.

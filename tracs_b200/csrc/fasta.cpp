@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <stdexcept>
@@ -69,6 +70,10 @@ const bool g_have_avx2 = __builtin_cpu_supports("avx2") != 0;
 struct FastaMachine {
   ByteBuf &ascii;
   std::vector<std::string> &names;
+  RowSink *sink = nullptr;      // completed records are handed over in batches while parsing goes on
+  uint64_t sink_row0 = 0;       // global number of this file's first record
+  uint64_t sunk = 0;            // records of this file already handed over
+  size_t base_len = 0;          // bytes of `ascii` in use before this file
   State st = SEEK;
   std::string name;
   uint64_t count = 0, L = 0;
@@ -77,7 +82,14 @@ struct FastaMachine {
   uint64_t qual_seen = 0;
   bool name_started = false, failed_len = false, truncated = false;
 
-  FastaMachine(ByteBuf &a, std::vector<std::string> &n) : ascii(a), names(n), len(a.size()), rec_start(a.size()) {}
+  FastaMachine(ByteBuf &a, std::vector<std::string> &n) : ascii(a), names(n), base_len(a.size()), len(a.size()), rec_start(a.size()) {}
+
+  // records [sunk, count) are complete and equally long: pass them on (at least `min_rows` at a time)
+  void flush_sink(uint64_t min_rows) {
+    if (!sink || failed_len || L == 0 || count - sunk < min_rows || count == sunk) return;
+    sink->rows(ascii.data() + base_len + sunk * L, sink_row0 + sunk, count - sunk, L);
+    sunk = count;
+  }
 
   void finish_record() {
     const uint64_t rec_len = len - rec_start;
@@ -86,6 +98,7 @@ struct FastaMachine {
     names.push_back(name);
     count++;
     rec_start = len;
+    flush_sink(std::max<uint64_t>(1, ((uint64_t)32 << 20) / std::max<uint64_t>(1, L)));  // ~32 MB batches
   }
 
   void feed(const unsigned char *p, const unsigned char *end) {
@@ -219,6 +232,7 @@ struct FastaMachine {
     ascii.len = len;
     if (failed_len) throw std::runtime_error("Error reading FASTA, variable sequence lengths!");
     if (truncated) throw std::runtime_error("Error reading FASTA!");
+    flush_sink(1);
   }
 };
 
@@ -298,7 +312,7 @@ size_t parallel_min_bytes() {
 
 // returns false when the file is not handled here (nothing appended); throws like the sequential reader
 bool read_fasta_parallel(const char *path, int n_threads, ByteBuf &ascii, std::vector<std::string> &names, uint64_t &L_io,
-                         uint64_t &count_out) {
+                         uint64_t &count_out, RowSink *sink, uint64_t row0) {
   Mapped m;
   m.fd = open(path, O_RDONLY);
   if (m.fd < 0) return false;
@@ -368,6 +382,7 @@ bool read_fasta_parallel(const char *path, int n_threads, ByteBuf &ascii, std::v
     if (tail_error) std::rethrow_exception(tail_error);
     ascii.reserve(ascii.size() + tail.size() + 16);
     memcpy(ascii.data() + ascii.size(), tail.data(), tail.size());
+    if (sink && tm.count > 0 && tm.L > 0) sink->rows(ascii.data() + ascii.size(), row0, tm.count, tm.L);
     ascii.len += tail.size();
     names.insert(names.end(), tail_names.begin(), tail_names.end());
     if (tm.count > 0) L_io = tm.L;
@@ -382,7 +397,14 @@ bool read_fasta_parallel(const char *path, int n_threads, ByteBuf &ascii, std::v
   ascii.reserve(base + (n_par + tail_count) * L + 16);
   std::vector<std::string> par_names(n_par);
   std::atomic<size_t> next(0);
-  std::atomic<int> not_simple(0), bad_len(0);
+  std::atomic<int> not_simple(0), bad_len(0), workers_left(T);
+  // rows are handed to the sink in chunks (~32 MB) as soon as every record of a chunk is parsed; the workers take
+  // the records in file order, so chunks complete (nearly) in order while later ones are still being parsed
+  const size_t chunk_rows = std::max<size_t>(1, ((size_t)32 << 20) / std::max<uint64_t>(1, L));
+  const size_t n_chunks = (n_par + chunk_rows - 1) / chunk_rows;
+  std::vector<std::atomic<uint32_t>> chunk_done(sink ? n_chunks : 0);
+  for (auto &c : chunk_done) c.store(0);
+  if (sink && L > 0) sink->expect(row0 + n_par + tail_count, L);
   {
     std::vector<std::thread> pool;
     uint8_t *out0 = ascii.data() + base;
@@ -398,12 +420,38 @@ bool read_fasta_parallel(const char *path, int n_threads, ByteBuf &ascii, std::v
               break;
             }
             if (nb != L) bad_len.store(1);
+            if (sink) chunk_done[r / chunk_rows].fetch_add(1, std::memory_order_release);
           }
         } catch (...) {  // out of memory while storing a name: let the sequential reader report it
           not_simple.store(1);
         }
+        workers_left.fetch_sub(1);
       });
+    bool sunk_any = false;
+    std::exception_ptr sink_error;
+    if (sink && L > 0) {
+      for (size_t c = 0; c < n_chunks; ++c) {
+        const size_t r0 = c * chunk_rows, nr = std::min(chunk_rows, n_par - r0);
+        while (chunk_done[c].load(std::memory_order_acquire) < nr && workers_left.load() > 0 && !not_simple.load() && !bad_len.load())
+          std::this_thread::sleep_for(std::chrono::microseconds(50));
+        if (chunk_done[c].load(std::memory_order_acquire) < nr || not_simple.load() || bad_len.load()) break;
+        try {
+          sink->rows(out0 + r0 * L, row0 + r0, nr, L);
+          sunk_any = true;
+        } catch (...) {
+          sink_error = std::current_exception();
+          not_simple.store(1);  // stops the workers
+          break;
+        }
+      }
+    }
     for (auto &th : pool) th.join();
+    if (sink_error) std::rethrow_exception(sink_error);
+    if (sink && (not_simple.load() || bad_len.load() || tail_error) && sunk_any) sink->reset();
+    else if (sink && L > 0 && !not_simple.load() && !bad_len.load() && !tail_error) {
+      // chunks the loop above did not reach (it only breaks on failure), then the records of the tail
+      if (tail_count) sink->rows(tail.data(), row0 + n_par, tail_count, L);
+    }
   }
   if (not_simple.load()) return false;  // `ascii.len` was never advanced: nothing appended
   if (bad_len.load()) throw std::runtime_error("Error reading FASTA, variable sequence lengths!");
@@ -419,7 +467,8 @@ bool read_fasta_parallel(const char *path, int n_threads, ByteBuf &ascii, std::v
 
 }  // namespace
 
-uint64_t read_fasta(const char *path, int n_threads, ByteBuf &ascii, std::vector<std::string> &names, uint64_t &L_io) {
+uint64_t read_fasta(const char *path, int n_threads, ByteBuf &ascii, std::vector<std::string> &names, uint64_t &L_io, RowSink *sink,
+                    uint64_t row0) {
   gzFile f = gzopen(path, "r");
   if (!f) throw std::runtime_error("Error reading FASTA!");
   const bool plain = gzdirect(f) != 0;
@@ -427,7 +476,7 @@ uint64_t read_fasta(const char *path, int n_threads, ByteBuf &ascii, std::vector
     uint64_t cnt = 0;
     bool done = false;
     try {
-      done = read_fasta_parallel(path, n_threads, ascii, names, L_io, cnt);
+      done = read_fasta_parallel(path, n_threads, ascii, names, L_io, cnt, sink, row0);
     } catch (...) {
       gzclose(f);
       throw;
@@ -446,6 +495,8 @@ uint64_t read_fasta(const char *path, int n_threads, ByteBuf &ascii, std::vector
   gzbuffer(f, 1 << 20);
   std::vector<unsigned char> buf((size_t(1) << 22) + 16);
   FastaMachine fm(ascii, names);
+  fm.sink = sink;
+  fm.sink_row0 = row0;
   for (;;) {
     int got = gzread(f, buf.data(), (unsigned)(buf.size() - 16));
     if (got < 0) {

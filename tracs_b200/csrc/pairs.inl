@@ -111,14 +111,19 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 __device__ __forceinline__ uint32_t pp_slot(uint32_t r) { return (r & 3u) * 16u + (r >> 2); }
 
 constexpr int BD_THREADS = 256;
+// MODE 0: rows = sample-major bit-planes (uint4 = A, C, G, T words of 32 sites); result = mismatches = 32 * Wp - matches.
+// MODE 1: rows = N-plane rows (uint4 = 128 sites); result = |N_x n N_y| (the dense-N variant of k_block_n: when most
+//         128-site blocks of most samples hold an N -- low-coverage metagenomic alignments, BASELINE configs[3] -- the
+//         summaries skip nothing and the intersection is a plain AND + POPC contraction over the whole row).
+template <int MODE>
 __global__ void __launch_bounds__(BD_THREADS, 2)
 k_block_d(const uint2 *__restrict__ tasks, const uint32_t *__restrict__ task_off, uint32_t n, const uint32_t *__restrict__ members,
           const uint32_t *__restrict__ comp_start, const uint32_t *__restrict__ size, const uint64_t *__restrict__ sq_off,
-          const uint4 *__restrict__ planesT, uint32_t Wp, uint32_t one, uint32_t *__restrict__ scratch_d) {
+          const uint4 *__restrict__ planesT, uint64_t Wp /* uint4 per row */, uint32_t one, uint32_t *__restrict__ scratch_d) {
   __shared__ __align__(16) uint4 sm[2][2][PP_KC * 64];  // [stage][side][kk * 64 + slot]: 32 KB
   const uint32_t tid = threadIdx.x;
   const uint32_t n_tasks = task_off[n];
-  const uint32_t nchunks = Wp / PP_KC;
+  const uint32_t nchunks = (uint32_t)(Wp / PP_KC);
   for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
     const uint2 t = tasks[task];
     const uint32_t c = t.x, br = t.y >> 16, bc = t.y & 0xFFFFu;
@@ -190,22 +195,27 @@ k_block_d(const uint2 *__restrict__ tasks, const uint32_t *__restrict__ task_off
           for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t mt = (r[i].x & cv[j].x) | (r[i].y & cv[j].y) | (r[i].z & cv[j].z) | (r[i].w & cv[j].w);
-              acc[i][j] = __popc(mt) * one + acc[i][j];
+              if (MODE == 0) {
+                const uint32_t mt = (r[i].x & cv[j].x) | (r[i].y & cv[j].y) | (r[i].z & cv[j].z) | (r[i].w & cv[j].w);
+                acc[i][j] = __popc(mt) * one + acc[i][j];
+              } else {
+                acc[i][j] = (__popc(r[i].x & cv[j].x) + __popc(r[i].y & cv[j].y)) * one + acc[i][j];
+                acc[i][j] = (__popc(r[i].z & cv[j].z) + __popc(r[i].w & cv[j].w)) * one + acc[i][j];
+              }
             }
         }
       }
       __syncthreads();
     }
     if (active) {
-      const uint32_t total_bits = Wp * 32u;
+      const uint32_t total_bits = (uint32_t)Wp * 32u;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t a = r0 + 4 * ty + i;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t b = c0 + 4 * tx + j;
-          if (a < b && b < m) scratch_d[sq + (uint64_t)a * m + b] = total_bits - acc[i][j];
+          if (a < b && b < m) scratch_d[sq + (uint64_t)a * m + b] = MODE == 0 ? total_bits - acc[i][j] : acc[i][j];
         }
       }
     }
@@ -411,12 +421,25 @@ static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  k_block_d<<<(unsigned)std::min<uint64_t>(task_cap, (uint64_t)n_sm * 16), BD_THREADS, 0, st>>>(tasks.p, task_off.p, n, members.p, comp_start.p,
-                                                                                              size.p, sq_off.p, g.planesT.p, g.Wp, 1u, scratch_d.p);
+  const unsigned bgrid = (unsigned)std::min<uint64_t>(task_cap, (uint64_t)n_sm * 16);
+  k_block_d<0><<<bgrid, BD_THREADS, 0, st>>>(tasks.p, task_off.p, n, members.p, comp_start.p, size.p, sq_off.p, g.planesT.p, g.Wp, 1u,
+                                           scratch_d.p);
   if (u_out) {
-    TRACS_CK(cudaMemsetAsync(scratch_i.p, 0, sq_cap * sizeof(uint32_t), st));
-    k_block_n<<<n_sm * 8, 256, 0, st>>>(dense_list.p, n_dense.p, members.p, comp_start.p, size.p, sq_off.p, g.nplane.p, g.npitch, g.nsum.p,
-                                      g.spitch, scratch_i.p);
+    // N intersections: summary-guided (k_block_n) while most 128-site blocks are free of N; a dense AND + POPC
+    // contraction over whole N-plane rows once they are not (estimated block occupancy 1 - (1 - p_N)^128 > 35 %)
+    const char *nmode = getenv("TRACS_NBLOCKS");  // "dense" / "sparse": tests force both
+    const double p_n = g.n && g.L ? (double)g.n_total / ((double)g.n * (double)g.L) : 0.0;
+    bool dense_n = 1.0 - pow(1.0 - std::min(1.0, p_n), 128.0) > 0.35;
+    if (nmode && !strcmp(nmode, "dense")) dense_n = true;
+    if (nmode && !strcmp(nmode, "sparse")) dense_n = false;
+    if (dense_n) {
+      k_block_d<1><<<bgrid, BD_THREADS, 0, st>>>(tasks.p, task_off.p, n, members.p, comp_start.p, size.p, sq_off.p,
+                                               reinterpret_cast<const uint4 *>(g.nplane.p), g.npitch / 4, 1u, scratch_i.p);
+    } else {
+      TRACS_CK(cudaMemsetAsync(scratch_i.p, 0, sq_cap * sizeof(uint32_t), st));
+      k_block_n<<<n_sm * 8, 256, 0, st>>>(dense_list.p, n_dense.p, members.p, comp_start.p, size.p, sq_off.p, g.nplane.p, g.npitch, g.nsum.p,
+                                        g.spitch, scratch_i.p);
+    }
   }
   k_pairs_gather<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, rank.p, size.p, sq_off.p, scratch_d.p, scratch_i.p, g.ncount.p, d_out,
                                          u_out);

@@ -1177,7 +1177,16 @@ struct Ingested {
   DevBuf<uint8_t> nsum;
   DevBuf<uint4> planes, planesT;
   bool partial_ambiguity = false;      // some variable site carries a 2- or 3-base IUPAC code
+  uint64_t n_total = 0;                // N / gap / unknown sites over all samples (sum of ncount)
 };
+
+__global__ void k_sum_u32(const uint32_t *__restrict__ v, uint64_t n, unsigned long long *out) {
+  unsigned long long s = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
 
 // ASCII matrix (device) -> N-plane + summaries + variable-site bit-planes (K0a + K0b)
 // `packed`: dev_seqs holds 4-bit masks, two sites per byte (pack4.inl), pitch in bytes
@@ -1332,10 +1341,17 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
       S.kernel_launches++;
     }
     TRACS_CK(cudaGetLastError());
+    DevBuf<unsigned long long> ntot(1);
+    TRACS_CK(cudaMemsetAsync(ntot.p, 0, 8, st));
+    k_sum_u32<<<64, 256, 0, st>>>(ncount.p, n, ntot.p);
+    S.kernel_launches++;
     uint32_t h_amb = 0;
+    unsigned long long h_ntot = 0;
     TRACS_CK(cudaMemcpyAsync(&h_amb, amb.p, 4, cudaMemcpyDeviceToHost, st));
+    TRACS_CK(cudaMemcpyAsync(&h_ntot, ntot.p, 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaStreamSynchronize(st));
     g.partial_ambiguity = h_amb != 0;
+    g.n_total = h_ntot;
   }
   S.ms_compact += T.stop();
   if (!keep_site_idx) site_idx.release();
