@@ -7,7 +7,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
-template <int N>
+template <int N, int PC = 0>
 __global__ void __launch_bounds__(128) rate(int reps, long long *out, int per_commit) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -34,6 +34,17 @@ __global__ void __launch_bounds__(128) rate(int reps, long long *out, int per_co
     const uint64_t da = make_desc(smem_u32(smem), 16 * 128, 128);
     const uint64_t db = make_desc(smem_u32(smem) + 128 * 32, (N / 8) * 128, 128);
     const long long t0 = clock64();
+    if (PC > 0) {
+      // compile-time commit spacing: PC MMAs (fully unrolled), then one commit -- no runtime division in the issue loop
+      for (int r = 0; r < reps; r += PC) {
+#pragma unroll
+        for (int q = 0; q < PC; ++q)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem), "l"(da), "l"(db),
+                       "r"(idesc), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&bars[(r / PC) & 1])) : "memory");
+      }
+    } else
     for (int r = 0; r < reps; ++r) {
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem), "l"(da), "l"(db),
@@ -64,6 +75,11 @@ int main() {
       cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
       printf("N=128 commit every %d MMAs: %.1f clk/MMA\n", pc, (double)h[1] / reps);
     }
+#define RUNPC(PCV)                                                                                         \
+    rate<128, PCV><<<1, 128, (128 + 128) * 32 + 1024>>>(1920, d, 0);                                       \
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);                                                          \
+    printf("N=128 commit every %d MMAs (compile-time): %.1f clk/MMA\n", PCV, (double)h[1] / 1920);
+    RUNPC(1) RUNPC(2) RUNPC(3) RUNPC(4) RUNPC(5) RUNPC(6) RUNPC(8) RUNPC(10) RUNPC(12) RUNPC(16) RUNPC(20) RUNPC(32)
     rate<128><<<1, 128, (128 + 128) * 32 + 1024>>>(reps, d, 0);
     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
     printf("N=128: issue %.1f clk/MMA, complete %.1f clk/MMA  (%s)\n", (double)h[0] / reps, (double)h[1] / reps, cudaGetErrorString(cudaGetLastError()));

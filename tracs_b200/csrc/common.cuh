@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <memory>
 #include <new>
 #include <stdexcept>
@@ -155,6 +156,10 @@ struct ByteBuf {
     if (!q) throw std::bad_alloc();
     p = q;
     cap = c;
+#ifdef MADV_HUGEPAGE
+    // multi-GB matrices written once by many parser threads: 2 MB pages cut the first-touch faults 512-fold
+    if (c >= ((size_t)8 << 20)) madvise((void *)(((uintptr_t)q + 4095) & ~(uintptr_t)4095), (c - 4096) & ~(size_t)4095, MADV_HUGEPAGE);
+#endif
   }
   uint8_t *data() { return p; }
   size_t size() const { return len; }

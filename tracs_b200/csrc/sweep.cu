@@ -447,7 +447,8 @@ k_gather(const uint8_t *__restrict__ seqs, uint64_t n, uint64_t pitch, const uin
       if (s >= s1) break;
       const uint32_t m = mk[t];
       // two- or three-base codes at a variable site rule out the one-hot GEMM identity (sweep_tc.inl)
-      if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) *amb_flag = 1u;
+      if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) atomicOr(amb_flag, 1u);
+      if (__any_sync(0xFFFFFFFFu, live && m == 15u) && lane == 0) atomicOr(amb_flag, 2u);  // an N at a variable site
       const uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
       const uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
       const uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
@@ -549,18 +550,20 @@ k_slice(const uint8_t *__restrict__ X, uint64_t XP, const uint8_t *__restrict__ 
     fast = __all_sync(0xFFFFFFFFu, a == base + lane && b == base + 32 + lane) && !(base & 0x80000000u) && (base & 15u) == 0;
   }
   if (fast) {
-    bool amb = false;
+    bool amb = false, hasn = false;
     for (uint64_t s = s0 + lane; s < s1; s += 32) {
       const uint4 *row = reinterpret_cast<const uint4 *>(X + s * XP + base);
       const uint4 q0 = __ldg(row), q1 = __ldg(row + 1), q2 = __ldg(row + 2), q3 = __ldg(row + 3);
       const uint4 pa = slice_word(q0, q1), pb = slice_word(q2, q3);
       amb |= slice_ambiguous(pa) | slice_ambiguous(pb);
+      hasn |= ((pa.x & pa.y & pa.z & pa.w) | (pb.x & pb.y & pb.z & pb.w)) != 0u;
       planes[w0 * Npad + s] = pa;
       planes[(w0 + 1) * Npad + s] = pb;
       planesT[s * Wp + w0] = pa;
       planesT[s * Wp + w0 + 1] = pb;
     }
-    if (__any_sync(0xFFFFFFFFu, amb) && lane == 0) *amb_flag = 1u;
+    if (__any_sync(0xFFFFFFFFu, amb) && lane == 0) atomicOr(amb_flag, 1u);
+    if (__any_sync(0xFFFFFFFFu, hasn) && lane == 0) atomicOr(amb_flag, 2u);
     return;
   }
   for (uint64_t w = w0; w < w0 + 2 && w * 32 < V; ++w) {
@@ -579,7 +582,8 @@ k_slice(const uint8_t *__restrict__ X, uint64_t XP, const uint8_t *__restrict__ 
         const uint64_t s = sb + t;
         if (s >= s1) break;
         const uint32_t m = mk[t];
-        if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) *amb_flag = 1u;
+        if (__any_sync(0xFFFFFFFFu, m != 15u && (m & (m - 1)) != 0u) && lane == 0) atomicOr(amb_flag, 1u);
+        if (__any_sync(0xFFFFFFFFu, live && m == 15u) && lane == 0) atomicOr(amb_flag, 2u);
         const uint32_t A = __ballot_sync(0xFFFFFFFFu, m & 1);
         const uint32_t C = __ballot_sync(0xFFFFFFFFu, m & 2);
         const uint32_t G = __ballot_sync(0xFFFFFFFFu, m & 4);
@@ -610,6 +614,7 @@ struct SweepArgs {
   uint32_t n_tiles;
   uint32_t cb_min;  // first col-block allowed by j_start
   const uint2 *tile_table;  // [n_tiles] (row-block, col-block) of every tile of the launch (k_tile_table)
+  const uint32_t *tc_ncnt;  // k_sweep_tc2<4>: per-sample N count over the swept words (k_tc_ncount), else null
   unsigned long long *counter;
   uint64_t *keys;
   uint32_t *dvals;
@@ -1138,21 +1143,40 @@ __global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t
 
 }  // namespace tracs
 #include "sweep_tc.inl"
+#include "sweep_tc2.inl"
 namespace tracs {
 
 // One launch of the tile sweep over a.n_tiles tiles and a.Wp words: tensor-core kernel when the masks
 // allow its identity (no 2-/3-base codes at variable sites), LOP3/POPC kernel otherwise.
-static void launch_tile_sweep(const SweepArgs &a, bool use_tc, cudaStream_t st) {
+// `has_n`: some variable site of some sample is N (ingest flag): the tensor-core kernel then needs its fourth plane.
+static void launch_tile_sweep(const SweepArgs &a_in, bool use_tc, cudaStream_t st, bool has_n = true) {
+  SweepArgs a = a_in;
   // the opt-in is per device (context): set on every call, it is a cheap driver call
   TRACS_CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
   TRACS_CK(cudaFuncSetAttribute(k_sweep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  TRACS_CK(cudaFuncSetAttribute(k_sweep_tc2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc2Geom<3>::SMEM));
+  TRACS_CK(cudaFuncSetAttribute(k_sweep_tc2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc2Geom<4>::SMEM));
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (a.n_tiles == 0) return;
   g_stats.tc_sweep = use_tc ? 1.0f : 0.0f;
-  if (use_tc) {
+  const char *tcv = getenv("TRACS_TC");  // "v1": the round-1 kernel (five one-hot planes), kept for comparison
+  DevBuf<uint32_t> ncnt;
+  if (use_tc && tcv && !strcmp(tcv, "v1")) {
     k_sweep_tc<<<(unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)n_sm), TC_THREADS, TC_SMEM, st>>>(a);
+  } else if (use_tc) {
+    const unsigned grid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)n_sm);
+    if (has_n) {
+      ncnt.alloc(a.Npad);
+      k_tc_ncount<<<(a.Npad + 255) / 256, 256, 0, st>>>(a.planes, a.Npad, a.Wp, ncnt.p);
+      g_stats.kernel_launches++;
+      a.tc_ncnt = ncnt.p;
+      k_sweep_tc2<4><<<grid, TC2_THREADS, Tc2Geom<4>::SMEM, st>>>(a);
+    } else {
+      a.tc_ncnt = nullptr;
+      k_sweep_tc2<3><<<grid, TC2_THREADS, Tc2Geom<3>::SMEM, st>>>(a);
+    }
   } else {
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep, SWEEP_THREADS, SWEEP_SMEM);
@@ -1178,6 +1202,7 @@ struct Ingested {
   DevBuf<uint4> planes, planesT;
   bool partial_ambiguity = false;      // some variable site carries a 2- or 3-base IUPAC code
   uint64_t n_total = 0;                // N / gap / unknown sites over all samples (sum of ncount)
+  bool has_n_var = true;               // some sample is N at some variable site (the tensor-core sweep needs its N plane)
 };
 
 __global__ void k_sum_u32(const uint32_t *__restrict__ v, uint64_t n, unsigned long long *out) {
@@ -1350,7 +1375,8 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
     TRACS_CK(cudaMemcpyAsync(&h_amb, amb.p, 4, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaMemcpyAsync(&h_ntot, ntot.p, 8, cudaMemcpyDeviceToHost, st));
     TRACS_CK(cudaStreamSynchronize(st));
-    g.partial_ambiguity = h_amb != 0;
+    g.partial_ambiguity = (h_amb & 1u) != 0;
+    g.has_n_var = (h_amb & 2u) != 0;
     g.n_total = h_ntot;
   }
   S.ms_compact += T.stop();
@@ -1570,7 +1596,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       for (uint32_t pw = first; pw && !refined; pw = pw < 16 ? 16 : (pw < PREFILTER_WORDS ? PREFILTER_WORDS : 0)) {
         a.Wp = pw;
         T.start();
-        launch_tile_sweep(a, tc_ok && pw > 16, st);
+        launch_tile_sweep(a, tc_ok && pw > 16, st, ing.has_n_var);
         S.ms_sweep += T.stop();
         S.n_tiles += n_tiles;
         S.swept_wordpairs += units[b].pairs * pw;
@@ -1619,7 +1645,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       if (o.sweep_variant == 2 && ing.partial_ambiguity)
         throw std::runtime_error("tensor-core sweep requested but the alignment has 2-/3-base IUPAC codes at variable sites");
       T.start();
-      launch_tile_sweep(a, tc_ok, st);
+      launch_tile_sweep(a, tc_ok, st, ing.has_n_var);
       S.ms_sweep += T.stop();
       S.n_tiles += n_tiles;
       S.swept_wordpairs += units[b].pairs * std::max<uint64_t>(W, 1);  // algorithmic words (padding not counted)
