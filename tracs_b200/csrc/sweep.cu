@@ -1144,6 +1144,7 @@ __global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t
 }  // namespace tracs
 #include "sweep_tc.inl"
 #include "sweep_tc2.inl"
+#include "sweep_tc3.inl"
 namespace tracs {
 
 // One launch of the tile sweep over a.n_tiles tiles and a.Wp words: tensor-core kernel when the masks
@@ -1166,16 +1167,35 @@ static void launch_tile_sweep(const SweepArgs &a_in, bool use_tc, cudaStream_t s
   if (use_tc && tcv && !strcmp(tcv, "v1")) {
     k_sweep_tc<<<(unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)n_sm), TC_THREADS, TC_SMEM, st>>>(a);
   } else if (use_tc) {
-    const unsigned grid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)n_sm);
+    a.tc_ncnt = nullptr;
     if (has_n) {
       ncnt.alloc(a.Npad);
       k_tc_ncount<<<(a.Npad + 255) / 256, 256, 0, st>>>(a.planes, a.Npad, a.Wp, ncnt.p);
       g_stats.kernel_launches++;
       a.tc_ncnt = ncnt.p;
-      k_sweep_tc2<4><<<grid, TC2_THREADS, Tc2Geom<4>::SMEM, st>>>(a);
+    }
+    if (tcv && !strcmp(tcv, "v2")) {  // 128 x 128 tiles (kept for comparison)
+      const unsigned grid = (unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)n_sm);
+      if (has_n) k_sweep_tc2<4><<<grid, TC2_THREADS, Tc2Geom<4>::SMEM, st>>>(a);
+      else k_sweep_tc2<3><<<grid, TC2_THREADS, Tc2Geom<3>::SMEM, st>>>(a);
     } else {
-      a.tc_ncnt = nullptr;
-      k_sweep_tc2<3><<<grid, TC2_THREADS, Tc2Geom<3>::SMEM, st>>>(a);
+      // 128 x 512 super-tiles: up to four consecutive tiles of a row-block share one expansion of the row panel
+      TRACS_CK(cudaFuncSetAttribute(k_sweep_tc3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc3Geom<3>::SMEM));
+      TRACS_CK(cudaFuncSetAttribute(k_sweep_tc3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc3Geom<4>::SMEM));
+      std::vector<uint32_t> h_prefix(a.n_rb + 1), sprefix(a.n_rb + 1, 0);
+      TRACS_CK(cudaMemcpyAsync(h_prefix.data(), a.tile_prefix, (a.n_rb + 1) * 4, cudaMemcpyDeviceToHost, st));
+      TRACS_CK(cudaStreamSynchronize(st));
+      for (uint32_t k = 0; k < a.n_rb; ++k) sprefix[k + 1] = sprefix[k] + (h_prefix[k + 1] - h_prefix[k] + 3) / 4;
+      const uint32_t n_stiles = sprefix[a.n_rb];
+      DevBuf<uint32_t> d_sprefix(a.n_rb + 1);
+      DevBuf<uint2> d_stiles(std::max<uint32_t>(1, n_stiles));
+      TRACS_CK(cudaMemcpyAsync(d_sprefix.p, sprefix.data(), (a.n_rb + 1) * 4, cudaMemcpyHostToDevice, st));
+      k_stile_table<<<(n_stiles + 255) / 256, 256, 0, st>>>(a.rb_list, d_sprefix.p, a.n_rb, a.cb_min, a.Npad / TILE, n_stiles, d_stiles.p);
+      g_stats.kernel_launches++;
+      const unsigned grid = (unsigned)std::min<uint64_t>(n_stiles, (uint64_t)n_sm);
+      if (has_n) k_sweep_tc3<4><<<grid, TC3_THREADS, Tc3Geom<4>::SMEM, st>>>(a, d_stiles.p, n_stiles);
+      else k_sweep_tc3<3><<<grid, TC3_THREADS, Tc3Geom<3>::SMEM, st>>>(a, d_stiles.p, n_stiles);
+      TRACS_CK(cudaStreamSynchronize(st));  // sprefix (host) and the tables go out of scope
     }
   } else {
     int occ = 1;

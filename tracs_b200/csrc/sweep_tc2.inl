@@ -114,12 +114,27 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_sweep_tc2(const SweepArgs a)
           *reinterpret_cast<uint4 *>(dst + (size_t)(2 * 3 + h) * ((TILE / 8) * 128)) = o;
         }
       };
+      // The panels of a full-length tile are tens of MB each and stream from HBM: two groups are held in registers
+      // ahead of the one being expanded and the lines of a group 16 further on are requested into L2 (the first
+      // version kept one group in flight and ran at DRAM latency per group, not at the MMA rate).
+      constexpr uint32_t PFD = 32;  // words between the L2 prefetch and the use
       uint4 c0 = __ldg(src), c1 = __ldg(src + (size_t)a.Npad);
+      uint4 e0 = c0, e1 = c1;
+      if (nw > 2) {
+        e0 = __ldg(src + (size_t)2 * a.Npad);
+        e1 = __ldg(src + (size_t)3 * a.Npad);
+      }
       for (uint32_t w = 0; w < nw; w += 2, ++gi_run) {
         const uint4 x0 = c0, x1 = c1;
-        if (w + 2 < nw) {
-          c0 = __ldg(src + (size_t)(w + 2) * a.Npad);
-          c1 = __ldg(src + (size_t)(w + 3) * a.Npad);
+        c0 = e0;
+        c1 = e1;
+        if (w + 4 < nw) {
+          e0 = __ldg(src + (size_t)(w + 4) * a.Npad);
+          e1 = __ldg(src + (size_t)(w + 5) * a.Npad);
+        }
+        if (w + PFD < nw && (lane & 7u) == 0) {  // one request per 128-byte line (8 rows x 16 B)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(w + PFD) * a.Npad));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(w + PFD + 1) * a.Npad));
         }
         const uint32_t g = gi_run % TC2_GROUPS;
         mbar_wait(&empty[g], ((gi_run / TC2_GROUPS) & 1u) ^ 1u);
