@@ -1193,8 +1193,10 @@ static void launch_tile_sweep(const SweepArgs &a_in, bool use_tc, cudaStream_t s
       k_stile_table<<<(n_stiles + 255) / 256, 256, 0, st>>>(a.rb_list, d_sprefix.p, a.n_rb, a.cb_min, a.Npad / TILE, n_stiles, d_stiles.p);
       g_stats.kernel_launches++;
       const unsigned grid = (unsigned)std::min<uint64_t>(n_stiles, (uint64_t)n_sm);
-      if (has_n) k_sweep_tc3<4><<<grid, TC3_THREADS, Tc3Geom<4>::SMEM, st>>>(a, d_stiles.p, n_stiles);
-      else k_sweep_tc3<3><<<grid, TC3_THREADS, Tc3Geom<3>::SMEM, st>>>(a, d_stiles.p, n_stiles);
+      const char *dbg_env = getenv("TRACS_TC3_DBG");  // timing experiments (profiles/r2_tc.md); never set in production
+      const uint32_t dbg = dbg_env ? (uint32_t)atoi(dbg_env) : 0u;
+      if (has_n) k_sweep_tc3<4><<<grid, TC3_THREADS, Tc3Geom<4>::SMEM, st>>>(a, d_stiles.p, n_stiles, dbg);
+      else k_sweep_tc3<3><<<grid, TC3_THREADS, Tc3Geom<3>::SMEM, st>>>(a, d_stiles.p, n_stiles, dbg);
       TRACS_CK(cudaStreamSynchronize(st));  // sprefix (host) and the tables go out of scope
     }
   } else {

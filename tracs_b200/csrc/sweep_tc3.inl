@@ -38,7 +38,9 @@ __global__ void k_stile_table(const uint32_t *__restrict__ rb_list, const uint32
 }
 
 template <int NP>
-__global__ void __launch_bounds__(TC3_THREADS, 1) k_sweep_tc3(const SweepArgs a, const uint2 *__restrict__ stiles, uint32_t n_stiles) {
+__global__ void __launch_bounds__(TC3_THREADS, 1) k_sweep_tc3(const SweepArgs a, const uint2 *__restrict__ stiles, uint32_t n_stiles,
+                                                              uint32_t dbg /* timing experiments only (TRACS_TC3_DBG, profiles/r2_tc.md): 1 no proxy fence, 2 no operand
+                                                                              loads, 4 no expansion arithmetic, 8 no MMAs -- results are wrong when set */) {
   using G = Tc3Geom<NP>;
   constexpr int S = G::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -89,57 +91,89 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_sweep_tc3(const SweepArgs a,
         const uint32_t sample = is_row[t] ? rb * TILE + r : cb0 * TILE + rB;
         live[t] = is_row[t] || ((rB >> 8) < nhalf && sample < a.Npad);
         src[t] = a.planes + (live[t] ? sample : 0u);
-        off[t] = is_row[t] ? (r >> 3) * 128u + (r & 7u) * 16u
-                           : G::A_BYTES + (rB >> 8) * G::BH_BYTES + ((rB & 255u) >> 3) * 128u + (rB & 7u) * 16u;
+        off[t] = is_row[t] ? (r >> 3) * 128u + (r & 7u) * 16u + h * 2048u
+                           : G::A_BYTES + (rB >> 8) * G::BH_BYTES + ((rB & 255u) >> 3) * 128u + (rB & 7u) * 16u + h * 4096u;
       }
-      auto expand = [&](const uint4 &x, uint8_t *dst, uint32_t kstride, uint32_t nmul) {
+      // One plane word half (16 sites) -> 16 operand bytes: the bits are masked in place into PRMT selector nibbles
+      // (bit 4k + q of the half -> byte k of register q; any fixed site permutation is fine as long as both operands
+      // use it) and PRMT picks +1 / -1 out of a two-register byte pool: 9 instructions per 16 bytes instead of 16.
+      // Stores go through explicit shared-space addresses (STS.128; the generic form cost 64-bit address arithmetic).
+      auto sts128 = [](uint32_t saddr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+      };
+      auto pm = [](uint32_t a, uint32_t b, uint32_t sel) {
+        uint32_t r;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+        return r;
+      };
+      auto expand = [&](const uint4 &x, uint32_t dst, uint32_t kstride, uint32_t nmul) {
         const uint32_t hi = x.z | x.w, lo = x.y | x.w;   // A = 00, C = 01, G = 10, T = 11
         const uint32_t pl[3] = {hi, lo, ~(hi ^ lo)};
-        const uint32_t nb = NP == 4 ? (x.x & x.y & x.z & x.w) : 0u;
-        uint32_t nm[4];
+        if (NP == 3) {
+          // selector 0 -> -1; 1, 2, 4 -> +1. The pool is derived from a kernel argument so that it lives in ONE register
+          // (as a literal the compiler re-materialised it in front of every PRMT: 16 extra instructions per word)
+          const uint32_t PA = 0x000101FEu + a.one, PB = a.one;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) nm[q] = ((nb >> (4 * h + q)) & 0x01010101u) * 0xFFu;
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          uint4 o;
-          uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t v = (((pl[p] >> (4 * h + q)) & 0x01010101u) * 0xFEu) ^ 0xFFFFFFFFu;  // bit 1 -> +1, bit 0 -> -1
-            if (NP == 4) v &= ~nm[q];
-            ow[q] = v;
+          for (int p = 0; p < 3; ++p) {
+            const uint32_t v = pl[p] >> (16u * h);
+            sts128(dst + 2 * p * kstride, pm(PA, PB, v & 0x1111u), pm(PA, PB, v & 0x2222u), pm(PA, PB, v & 0x4444u),
+                   pm(PA, PB, (v >> 3) & 0x1111u));
           }
-          *reinterpret_cast<uint4 *>(dst + (size_t)(2 * p + h) * kstride) = o;
-        }
-        if (NP == 4) {
-          uint4 o;
-          o.x = (nm[0] & 0x01010101u) * nmul; o.y = (nm[1] & 0x01010101u) * nmul;
-          o.z = (nm[2] & 0x01010101u) * nmul; o.w = (nm[3] & 0x01010101u) * nmul;
-          *reinterpret_cast<uint4 *>(dst + (size_t)(2 * 3 + h) * kstride) = o;
+        } else {
+          const uint32_t nb = x.x & x.y & x.z & x.w;
+          uint32_t nm[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) nm[q] = ((nb >> (4 * h + q)) & 0x01010101u) * 0xFFu;  // 0xFF in the bytes of N sites
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = ((((pl[p] >> (4 * h + q)) & 0x01010101u) * 0xFEu) ^ 0xFFFFFFFFu) & ~nm[q];
+            sts128(dst + 2 * p * kstride, o[0], o[1], o[2], o[3]);
+          }
+          sts128(dst + 2 * 3 * kstride, (nm[0] & 0x01010101u) * nmul, (nm[1] & 0x01010101u) * nmul, (nm[2] & 0x01010101u) * nmul,
+                 (nm[3] & 0x01010101u) * nmul);
         }
       };
+      // Operand words: the load of word w + 1 is issued before word w is expanded and must have RETURNED by the proxy
+      // fence that closes the expansion (the fence is a CTA-wide memory barrier and waits for this thread's outstanding
+      // loads: with two words in flight it exposed a DRAM round trip per word, profiles/r2_tc.md). So the loads are made
+      // L2 hits: the lines of word w + PFD are requested into L2 well ahead, one request per 128-byte line.
+      constexpr uint32_t PFD = 24;
+      const bool pf_lane = (lane & 0x17u) == 0u;  // lanes 0 and 8: the two lines of this warp's 16 rows
+      const uint32_t sbase_u32 = smem_u32(stage_base);
       const uint4 zero = make_uint4(0, 0, 0, 0);
-      uint4 c[2], e[2];
+      uint4 c[2];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         c[t] = live[t] ? __ldg(src[t]) : zero;
-        e[t] = (live[t] && nw > 1) ? __ldg(src[t] + (size_t)a.Npad) : zero;
+        if (live[t] && pf_lane)
+          for (uint32_t w = 1; w < PFD && w < nw; ++w) asm volatile("prefetch.global.L2 [%0];" ::"l"(src[t] + (size_t)w * a.Npad));
       }
+#pragma unroll 2
       for (uint32_t w = 0; w < nw; ++w, ++it) {
         uint4 x[2];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           x[t] = c[t];
-          c[t] = e[t];
-          if (live[t] && w + 2 < nw) e[t] = __ldg(src[t] + (size_t)(w + 2) * a.Npad);
+          if (live[t] && w + 1 < nw && !(dbg & 2u)) c[t] = __ldg(src[t] + (size_t)(w + 1) * a.Npad);
+          if (live[t] && pf_lane && w + PFD < nw) asm volatile("prefetch.global.L2 [%0];" ::"l"(src[t] + (size_t)(w + PFD) * a.Npad));
         }
         const uint32_t s = it % S;
         mbar_wait(&empty[s], ((it / S) & 1u) ^ 1u);
-        uint8_t *sb = stage_base + (size_t)s * G::STAGE_BYTES;
+        const uint32_t sb = sbase_u32 + s * G::STAGE_BYTES;
 #pragma unroll
         for (int t = 0; t < 2; ++t)
-          if (live[t]) expand(x[t], sb + off[t], is_row[t] ? 2048u : 4096u, is_row[t] ? 0xFDu : 1u);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
+          if (live[t]) {
+            if (dbg & 4u) {
+              sts128(sb + off[t], x[t].x, x[t].y, x[t].z, x[t].w);
+              sts128(sb + off[t] + 2 * (is_row[t] ? 2048u : 4096u), x[t].x, x[t].y, x[t].z, x[t].w);
+              sts128(sb + off[t] + 4 * (is_row[t] ? 2048u : 4096u), x[t].x, x[t].y, x[t].z, x[t].w);
+            } else {
+              expand(x[t], sb + off[t], is_row[t] ? 2048u : 4096u, is_row[t] ? 0xFDu : 1u);
+            }
+          }
+        if (!(dbg & 1u)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
       }
@@ -155,7 +189,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_sweep_tc3(const SweepArgs a,
           mbar_wait(&full[s], (it / S) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st0 = sbase + s * G::STAGE_BYTES;
-          for (uint32_t b = 0; b < nhalf; ++b) {
+          for (uint32_t b = 0; b < ((dbg & 8u) ? 0u : nhalf); ++b) {
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
               const uint64_t da = umma_desc(st0 + p * 2 * 2048, 2048, 128);
