@@ -269,3 +269,38 @@ def test_fasta_entry_point_streams_rows_to_the_device(oracle_mod, tmp_path, monk
     synth.write_fasta(bad, s[:5, :1000])
     with pytest.raises(RuntimeError, match="variable sequence lengths"):
         tracs_b200.pairsnp(fasta=[p1, bad], n_threads=2, dist=40, filter=False)
+
+
+def test_sigint_between_bands_unwinds_the_call(tmp_path):
+    """Ctrl-C during a long sweep (reference: 'Interrupted by user!' + exit(1), src/pairsnp.hpp:434-441): the library's
+    own handler raises a flag, the band loop sees it, the call returns status 4 -> KeyboardInterrupt with that message;
+    the previous SIGINT disposition is restored."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import os, signal, sys, threading, time, torch
+sys.path.insert(0, %r)
+import tracs_b200
+n, L = 60000, 40000
+pitch = L // 2
+buf = torch.empty(n * pitch, dtype=torch.uint8, device="cuda")
+tracs_b200.synth_device(buf.data_ptr(), n, L, pitch, seed=9, p_var=1.0, n_clusters=n, mu=0.0, p_N=0.0, gc=0.5, gaps=0, packed=True)
+tracs_b200.pairsnp_packed(buf.data_ptr(), 2000, L, pitch, dist=2047)          # warm-up (contexts, caches)
+t0 = time.perf_counter()
+tracs_b200.pairsnp_packed(buf.data_ptr(), n, L, pitch, dist=2047, full_sweep=True)   # unselective: banded full-length sweeps
+t_full = time.perf_counter() - t0
+threading.Timer(min(0.15, t_full / 4), lambda: os.kill(os.getpid(), signal.SIGINT)).start()
+t0 = time.perf_counter()
+try:
+    tracs_b200.pairsnp_packed(buf.data_ptr(), n, L, pitch, dist=2047, full_sweep=True)
+    print("NOT-INTERRUPTED")
+except KeyboardInterrupt as ex:
+    print("INTERRUPTED", str(ex), "%%.3f %%.3f" %% (time.perf_counter() - t0, t_full))
+assert signal.getsignal(signal.SIGINT) is signal.default_int_handler
+r = tracs_b200.pairsnp_packed(buf.data_ptr(), 3000, L, pitch, dist=2047)     # the library is usable afterwards
+print("AFTER", len(r["rows"]))
+''' % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "INTERRUPTED Interrupted by user!" in out.stdout and "AFTER" in out.stdout, out.stdout + out.stderr
+    took, full = map(float, out.stdout.split("INTERRUPTED Interrupted by user!")[1].split()[:2])
+    assert took < full, (took, full)

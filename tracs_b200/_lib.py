@@ -121,6 +121,8 @@ def check(rc):
     msg = lib().tracs_last_error().decode(errors="replace")
     if rc == 3:
         raise IndexError(msg)
+    if rc == 4:     # SIGINT arrived during the call (the library checks between bands / chunks)
+        raise KeyboardInterrupt(msg)
     raise RuntimeError(msg)
 
 

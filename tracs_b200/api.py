@@ -19,7 +19,13 @@ def pairsnp(fasta, n_threads, dist, filter):
     fasta = [os.fspath(p) for p in fasta]
     paths = (C.c_char_p * max(1, len(fasta)))(*[os.fsencode(p) for p in fasta])
     e = Edges()
-    _lib.check(_lib.lib().tracs_pairsnp(paths, len(fasta), int(n_threads), int(dist), int(bool(filter)), C.byref(e)))
+    try:
+        _lib.check(_lib.lib().tracs_pairsnp(paths, len(fasta), int(n_threads), int(dist), int(bool(filter)), C.byref(e)))
+    except KeyboardInterrupt:
+        # the reference prints this and calls exit(1) from inside the extension (src/pairsnp.hpp:207-214, 434-441)
+        import sys
+        sys.stderr.write("Interrupted by user!\n")
+        raise SystemExit(1)
     r = _lib.take_edges(e, as_lists=True)
     return (r["rows"], r["cols"], r["dist"], r["names"], r["filt"], r["ncomp"])
 

@@ -1,6 +1,7 @@
 // C ABI of libtracs_b200.so (see include/tracs_b200.h for the contract and reference citations).
 #include <cub/cub.cuh>
 #include <math.h>
+#include <signal.h>
 #include <string.h>
 
 #include <algorithm>
@@ -153,6 +154,36 @@ void host_pool_free(void *p) {
     }
   }
   free(p);
+}
+
+// ---- SIGINT during a call ---------------------------------------------------------------------------------
+namespace {
+volatile sig_atomic_t g_sigint = 0;
+int g_scope_depth = 0;
+struct sigaction g_prev_action;
+void on_sigint(int) { g_sigint = 1; }
+}  // namespace
+
+InterruptScope::InterruptScope() {
+  const char *env = getenv("TRACS_SIGINT");
+  if (env && !strcmp(env, "0")) return;
+  if (g_scope_depth++ == 0) {
+    g_sigint = 0;
+    struct sigaction sa;
+    memset(&sa, 0, sizeof sa);
+    sa.sa_handler = on_sigint;
+    sigemptyset(&sa.sa_mask);
+    sa.sa_flags = SA_RESTART;
+    sigaction(SIGINT, &sa, &g_prev_action);
+  }
+}
+InterruptScope::~InterruptScope() {
+  const char *env = getenv("TRACS_SIGINT");
+  if (env && !strcmp(env, "0")) return;
+  if (--g_scope_depth == 0) sigaction(SIGINT, &g_prev_action, nullptr);
+}
+void check_interrupt() {
+  if (g_sigint) throw Interrupted{};
 }
 
 void require_device() {
@@ -484,6 +515,7 @@ static void stream_host_to_packed(const uint8_t *seqs, size_t n, size_t L, size_
   for (size_t r0 = 0; r0 < n; r0 += R, ++c) {
     const int b = (int)(c & 1);
     const size_t nr = std::min(R, n - r0);
+    check_interrupt();
     if (c >= 2) TRACS_CK(cudaStreamWaitEvent(cp, ev_free[b], 0));  // the encode that last read this buffer is done
     h2d_rows(stage[b], apitch, seqs + r0 * hpitch, hpitch, L, nr, cp);
     TRACS_CK(cudaEventRecord(ev_copied[b], cp));
@@ -561,6 +593,7 @@ struct DeviceRowStreamer : RowSink {
     }
     if (Lr != L) throw std::runtime_error("Error reading FASTA, variable sequence lengths!");
     if (first_row != n_rows) throw std::runtime_error("internal error: rows streamed out of order");
+    check_interrupt();
     reserve_rows(first_row + count);
     const uint64_t R = std::max<uint64_t>(1, slot_bytes / apitch);
     for (uint64_t r0 = 0; r0 < count; r0 += R) {
@@ -598,6 +631,7 @@ int tracs_pairsnp_packed(const uint8_t *dev_nib, size_t n, size_t L, size_t pitc
   memset(&g_stats, 0, sizeof g_stats);
   return guarded([&] {
     require_device();
+    InterruptScope sigint;
     tracs_opts_t o = normalise(opts, n);
     o.packed_input = 1;
     HostEdges he;
@@ -627,6 +661,7 @@ int tracs_pairsnp_device(const uint8_t *dev_seqs, size_t n, size_t L, size_t pit
   memset(&g_stats, 0, sizeof g_stats);
   return guarded([&] {
     require_device();
+    InterruptScope sigint;
     tracs_opts_t o = normalise(opts, n);
     HostEdges he;
     sweep_device(dev_seqs, n, L, pitch, o, he, 0);
@@ -640,6 +675,7 @@ int tracs_pairsnp_host(const uint8_t *seqs, size_t n, size_t L, size_t pitch, co
   memset(&g_stats, 0, sizeof g_stats);
   return guarded([&] {
     require_device();
+    InterruptScope sigint;
     tracs_opts_t o = normalise(opts, n);
     HostEdges he;
     const char *mode = getenv("TRACS_HOST_INGEST");  // "ascii": keep the ASCII matrix resident and pack it directly
@@ -669,6 +705,7 @@ int tracs_pairsnp(const char *const *paths, int n_paths, int n_threads, int32_t 
     // src/pairsnp.hpp:340-343
     if (n_paths < 1 || n_paths > 2) throw std::runtime_error("Invalid number of fasta files!");
     require_device();
+    InterruptScope sigint;
     // The reader hands completed rows to the device while it is still parsing (DeviceRowStreamer): host -> device
     // copies and the ASCII -> nibble encode overlap the parse; the pair sweep starts on the resident packed alignment
     // as soon as the last record is in. TRACS_FASTA_STREAM=0: parse everything first, then copy (tests compare).

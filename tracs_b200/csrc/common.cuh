@@ -43,12 +43,29 @@ void dev_cache_free(void *p);
 
 void require_device();  // throws unless a CUDA device is usable (there is no CPU fallback)
 
-// C-ABI status codes: 0 ok, 1 runtime error, 2 CUDA error, 3 index/range error
+// Ctrl-C during a long call (reference: PyErr_CheckSignals in its loops, then "Interrupted by user!" and exit(1),
+// src/pairsnp.hpp:207-214, 434-441). The compute entry points install a SIGINT handler for their duration
+// (InterruptScope) that only raises a flag; the sweep checks it between bands / chunks and unwinds with
+// status 4, which the Python bindings turn into KeyboardInterrupt (drop-in pairsnp: message + exit code 1).
+struct Interrupted {};
+struct InterruptScope {
+  InterruptScope();
+  ~InterruptScope();
+  InterruptScope(const InterruptScope &) = delete;
+  InterruptScope &operator=(const InterruptScope &) = delete;
+};
+void check_interrupt();  // throws Interrupted if SIGINT arrived since the innermost scope began
+
+// C-ABI status codes: 0 ok, 1 runtime error, 2 CUDA error, 3 index/range error, 4 interrupted (SIGINT)
 template <typename F>
 static int guarded(F &&f) {
   try {
     f();
     return 0;
+  } catch (const Interrupted &) {
+    set_error("Interrupted by user!");
+    cudaDeviceSynchronize();
+    return 4;
   } catch (const CudaError &e) {
     set_error(e.msg);
     cudaGetLastError();

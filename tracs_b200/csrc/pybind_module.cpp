@@ -7,6 +7,8 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <stdio.h>
+
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -21,6 +23,11 @@ void check(int rc) {
   if (rc == 0) return;
   const std::string msg = tracs_last_error();
   if (rc == 3) throw py::index_error(msg);  // std::out_of_range -> IndexError, like pybind11's own translation
+  if (rc == 4) {                            // SIGINT during the call: the reference prints this and exits with status 1
+    fprintf(stderr, "Interrupted by user!\n");
+    PyErr_SetObject(PyExc_SystemExit, py::int_(1).ptr());
+    throw py::error_already_set();
+  }
   throw std::runtime_error(msg);            // -> RuntimeError
 }
 

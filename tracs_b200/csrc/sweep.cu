@@ -1579,6 +1579,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
   bool fall_back = false;
 
   for (size_t b = 0; b < units.size(); ++b) {
+    check_interrupt();  // Ctrl-C between bands (reference: PyErr_CheckSignals per row, src/pairsnp.hpp:385, 434-441)
     std::vector<uint32_t> rbs(my_rb.begin() + units[b].first, my_rb.begin() + units[b].last);
     std::vector<uint32_t> prefix(rbs.size() + 1, 0);
     for (size_t k = 0; k < rbs.size(); ++k) prefix[k + 1] = prefix[k] + (n_cb - std::max(rbs[k], cb_min));
