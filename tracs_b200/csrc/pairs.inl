@@ -330,12 +330,19 @@ k_pairs_sparse(const uint64_t *__restrict__ keys, uint64_t n_keys, const uint32_
                const uint4 *__restrict__ planesT, uint32_t Wp, const uint32_t *__restrict__ nplane, uint64_t npitch,
                const uint8_t *__restrict__ nsum, uint64_t spitch, const uint32_t *__restrict__ ncount, uint32_t *__restrict__ d_out,
                uint32_t *__restrict__ u_out) {
-  const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  if (e >= n_keys) return;
+  // every lane pre-screens one candidate (most belong to components evaluated as blocks), then the warp works through
+  // the remaining ones together
+  const uint64_t e0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (e0 >= n_keys) return;
+  const uint64_t mine = e0 + lane;
+  const bool todo = mine < n_keys && !(dense && dense[root[keys[mine] >> 32]]);
+  uint32_t pending = __ballot_sync(0xFFFFFFFFu, todo);
+  while (pending) {
+  const uint64_t e = e0 + (uint32_t)(__ffs(pending) - 1);
+  pending &= pending - 1;
   const uint64_t k = keys[e];
   const uint64_t i = k >> 32, j = k & 0xFFFFFFFFull;
-  if (dense && dense[root[i]]) return;
   const uint4 *ri = planesT + i * Wp, *rj = planesT + j * Wp;
   uint32_t mism = 0;
 #pragma unroll 4
@@ -368,6 +375,7 @@ k_pairs_sparse(const uint64_t *__restrict__ keys, uint64_t n_keys, const uint32_
     d_out[e] = mism;
     if (u_out) u_out[e] = ncount[i] + ncount[j] - inter;
   }
+  }
 }
 
 // keys: E candidate keys (i << 32 | j, i < j), any order, no duplicates. d_out[e] = mismatches of the pair over all
@@ -381,7 +389,7 @@ static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint
   const bool blocks = !(mode && !strcmp(mode, "sparse")) && E < (1ull << 31);
   auto grid1 = [](uint64_t items) { return (unsigned)((items + 255) / 256); };
   if (!blocks) {
-    k_pairs_sparse<<<grid1(E * 32), 256, 0, st>>>(keys, E, nullptr, nullptr, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
+    k_pairs_sparse<<<grid1(E), 256, 0, st>>>(keys, E, nullptr, nullptr, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
                                                 g.ncount.p, d_out, u_out);
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
@@ -443,7 +451,7 @@ static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint
   }
   k_pairs_gather<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, rank.p, size.p, sq_off.p, scratch_d.p, scratch_i.p, g.ncount.p, d_out,
                                          u_out);
-  k_pairs_sparse<<<grid1(E * 32), 256, 0, st>>>(keys, E, parent.p, dense.p, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
+  k_pairs_sparse<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
                                               g.ncount.p, d_out, u_out);
   S.kernel_launches += 18 + (end_bit + 7) / 8;
   TRACS_CK(cudaGetLastError());

@@ -1116,7 +1116,8 @@ __global__ void k_trans_mark(const uint64_t *__restrict__ keys, const uint32_t *
   if (e >= E) return;
   const uint64_t k = keys[e];
   const int32_t dd = abs(days[k >> 32] - days[k & 0xFFFFFFFFull]);
-  used[(uint64_t)dvals[e] * DD + (uint32_t)dd] = 1;
+  uint8_t *u = used + (uint64_t)dvals[e] * DD + (uint32_t)dd;
+  if (!*u) *u = 1;  // millions of edges share a few thousand keys: read first, the stores all hit the same lines
 }
 __global__ void k_trans_table(const uint32_t *__restrict__ key_idx, const uint64_t *__restrict__ n_keys, uint32_t DD,
                               const double *__restrict__ lg, double lamb, double beta, double thr,
