@@ -11,7 +11,8 @@ B200, so it is the workload at EVERY GPU count:
   --gpus N      STRONG scaling of that one alignment ("scaling": "strong"): rank r holds the column slab
                 [L*r/N, L*(r+1)/N) of every sequence (tracs_b200/sites.py): per-slab ingest + prefilter of the
                 rank's triangle row-blocks, candidate all-gather, per-slab partial d / |N u N| for all candidates,
-                all-reduce, native finish on rank 0. Collectives: NCCL all-gather + all-reduce, O(candidates).
+                reduce-scatter, native finish of one slice per rank into a shared page-locked host table.
+                Collectives: NCCL all-gather + reduce-scatter, O(candidates).
   step          one whole pass of the hot path: packed alignment (resident in HBM) -> column masks + N planes ->
                 variable-site bit-planes -> all-pairs tile sweep with fused threshold -> ordered edge list ->
                 compared-site counts -> transmission likelihood -> edge columns on the host of rank 0.
@@ -70,8 +71,8 @@ def config_block(w, cfg_name, world):
     n, L = w["n"], w["L"]
     if cfg_name == "C3" and world > 1:
         par = ("site-sharded strong scaling of ONE alignment: rank r ingests columns [L*r/%d, L*(r+1)/%d) of every sequence and "
-               "prefilters its triangle row-blocks; candidates all-gathered, per-slab partial d and |N u N| all-reduced (NCCL), "
-               "finish on rank 0" % (world, world))
+               "prefilters its triangle row-blocks; candidates all-gathered, per-slab partial d and |N u N| reduce-scattered (NCCL), "
+               "every rank finishes a slice of the edges and copies it into one shared page-locked host table" % (world, world))
     elif world > 1:
         par = "%d independent replicas of the workload, one per GPU (no exchange)" % world
     else:
@@ -568,14 +569,16 @@ def main():
             "parity_spot_checks": spot_checks(inp, res, w["dist"]) if not strong else None,
         }
         if strong:
-            line["collectives"] = ["ncclAllGather (candidate counts + keys)", "ncclAllReduce (partial d, |N u N|)"]
+            line["collectives"] = ["ncclAllGather (candidate counts + keys)", "ncclReduceScatter (partial d, |N u N|)",
+                                   "ncclAllGather (edge counts per slice)", "barrier (slices landed in the shared host table)"]
     if strong and args.profile_phases:
         _, stp = sites.sweep(torch, dist_mod, device, rank, world, inp.buf.data_ptr(), n, inp.Ls, inp.pitch, L, w["dist"], days=inp.days,
                              lamb=w["lamb"], beta=w["beta"], threshold_Ek=w["threshold_Ek"], packed=inp.packed, profile=True)
         if rank == 0:
             line["stages_ms"]["phases_ms_rank0"] = stp.get("phases_ms")
-        # ---- the same tile kernels forced over the full length (what an unthresholded / dense run executes) ----------
-        if world == 1 and not args.no_extra:
+    # ---- the same tile kernels forced over the full length (what an unthresholded / dense run executes) ----------
+    if rank == 0 and world == 1 and not args.no_extra:
+        if True:
             for nm, variant in (("k_sweep_full_length", True), ("k_sweep_tc_full_length", "tc")):
                 try:
                     torch.cuda.synchronize()
