@@ -88,11 +88,11 @@ def test_prefilter_refine_and_fallback(oracle_mod, n_clusters, dist, expect):
     _cmp(res, oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4))
     assert st["n_words"] >= 256
     if expect == "refine":
-        # dist 0 / 20: the first window (8 words = 256 variable sites) is enough
-        assert st["ms_refine"] > 0 and st["swept_wordpairs"] == st["n_pairs"] * 8
+        # dist 0 / 20: the first window (4 words = 128 variable sites) is enough
+        assert st["ms_refine"] > 0 and st["swept_wordpairs"] == st["n_pairs"] * 4
     elif expect == "fallback":
-        # too many pairs survive the 8-, 16- and 64-word windows: three attempts, then the full-length sweep
-        assert st["ms_refine"] == 0 and st["n_candidates"] > 0 and st["swept_wordpairs"] > st["n_pairs"] * (8 + 16 + 64)
+        # too many pairs survive the 4-, 8-, 16- and 64-word windows: four attempts, then the full-length sweep
+        assert st["ms_refine"] == 0 and st["n_candidates"] > 0 and st["swept_wordpairs"] > st["n_pairs"] * (4 + 8 + 16 + 64)
     full = tracs_b200.pairsnp_matrix(s, dist=dist, full_sweep=True)
     st2 = tracs_b200.last_stats()
     assert st2["n_candidates"] == 0 and st2["ms_refine"] == 0

@@ -200,10 +200,10 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
     for (uint64_t p : plan.rb_pairs) my_pairs += p;
     g_stats.n_pairs = my_pairs;
     unsigned long long nc = 0;
-    // windows of 8, 16, 64 local words (any prefix of the slab's words gives a lower bound of d), widened while more
+    // windows of 4, 8, 16, 64 local words (any prefix of the slab's words gives a lower bound of d), widened while more
     // than 4 % of this rank's pairs survive; Wp is a multiple of KC. Kernel choice as in sweep_device.
-    const uint32_t first = o.dist < 32 ? 8u : prefilter_words(o.dist);
-    for (uint32_t pw = first;; pw = pw < 16 ? 16 : PREFILTER_WORDS) {
+    const uint32_t first = first_window(o.dist);
+    for (uint32_t pw = first;; pw = pw < 8 ? 8 : pw < 16 ? 16 : PREFILTER_WORDS) {
       const uint32_t words = std::min<uint32_t>(pw, g.Wp);
       TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
       size_t k0 = 0;

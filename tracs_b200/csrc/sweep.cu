@@ -686,6 +686,14 @@ static inline uint32_t prefilter_words(int64_t dist) {
   const uint64_t w = ((uint64_t)(dist + 1) * 8 + 31) / 32;
   return (uint32_t)std::min<uint64_t>(PREFILTER_WORDS, std::max<uint64_t>(16, round_up(w, 16)));
 }
+// Windows tried in turn by the filter-and-refine path: 4, 8, 16, 64 words (128 ... 2048 variable sites), starting where
+// the window holds about six sites per allowed SNP (dist <= 20: 4 words). A failed attempt costs its own sweep only.
+static inline uint32_t first_window(int64_t dist) {
+  if (dist < 22) return 4;
+  if (dist < 43) return 8;
+  return prefilter_words(dist);
+}
+static inline uint32_t next_window(uint32_t pw) { return pw < 8 ? 8 : pw < 16 ? 16 : (pw < PREFILTER_WORDS ? PREFILTER_WORDS : 0); }
 constexpr size_t SWEEP_SMEM = (size_t)STAGES * 2 * STAGE_U4 * sizeof(uint4);
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
@@ -703,7 +711,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
   }
   __syncthreads();
 
-  const uint32_t nk = a.Wp / KC;
+  // a window narrower than one stage (Wp = 4): one chunk per tile of which only the first Wp words are evaluated (the
+  // copies still bring KC words; the planes always hold at least KC)
+  const uint32_t nk = (a.Wp + KC - 1) / KC;
+  const int kc_used = a.Wp < (uint32_t)KC ? (int)a.Wp : KC;
   const uint32_t one = a.one;
   // The panels of ALL tiles of this CTA form one stream of chunks g = tile_iter * nk + c (stage = g % STAGES, parity =
   // (g / STAGES) & 1): chunk g + STAGES is requested as soon as chunk g has been consumed, whichever tile it belongs to,
@@ -757,7 +768,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
       const uint4 *pr = srow + (size_t)slot * STAGE_U4 + ty;
       const uint4 *pc = scol + (size_t)slot * STAGE_U4 + tx;
 #pragma unroll 2
-      for (int kk = 0; kk < KC; ++kk) {
+      for (int kk = 0; kk < kc_used; ++kk) {
         uint4 r[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) r[i] = pr[kk * TILE + i * 16];
@@ -1609,15 +1620,15 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
     bool handled = false;
     if (prefilter_mode) {
       // Filter-and-refine: tile-sweep only the first words of every pair; d is monotone in the number of sites, so a
-      // pair whose partial distance already exceeds `dist` is decided. Windows of 8, 16 and 64 words are tried in turn
-      // until <= 4 % of the pairs survive; those are finished per pair (k_refine). If even the widest window is not
-      // selective the call falls back to banded full-length sweeps (cost of the failed attempts: 88 / Wp).
+      // pair whose partial distance already exceeds `dist` is decided. Windows of 4, 8, 16 and 64 words are tried in turn
+      // until <= 4 % of the pairs survive; those are finished per component / per pair (pairs.inl). If even the widest
+      // window is not selective the call falls back to banded full-length sweeps (cost of the failed attempts: 92 / Wp).
       // Short windows run on the LOP3/POPC kernel (the tensor-core kernel pays its per-tile pipeline fill and its
       // TMEM epilogue on every 128 x 128 tile: measured equal at 16 words, slower below), the 64-word one on the
       // tensor cores when the masks allow it.
       bool refined = false;
-      const uint32_t first = o.dist < 32 ? 8u : prefilter_words(o.dist);
-      for (uint32_t pw = first; pw && !refined; pw = pw < 16 ? 16 : (pw < PREFILTER_WORDS ? PREFILTER_WORDS : 0)) {
+      const uint32_t first = first_window(o.dist);
+      for (uint32_t pw = first; pw && !refined; pw = next_window(pw)) {
         a.Wp = pw;
         T.start();
         launch_tile_sweep(a, tc_ok && pw > 16, st, ing.has_n_var);
