@@ -247,11 +247,16 @@ k_block_n(const uint32_t *__restrict__ dense_list, const uint32_t *__restrict__ 
           const uint32_t *__restrict__ comp_start, const uint32_t *__restrict__ size, const uint64_t *__restrict__ sq_off,
           const uint32_t *__restrict__ nplane, uint64_t npitch, const uint8_t *__restrict__ nsum, uint64_t spitch,
           uint32_t *__restrict__ scratch_i) {
+  // per thread: the members (index in the component) met so far with an N in this thread's block; a member that
+  // shares a site with an earlier one only has to look at those instead of walking over all earlier members
+  constexpr int HIST = 28;
+  __shared__ uint16_t s_hist[HIST][256];
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint64_t nq = spitch / 4;
   const uint64_t total = (uint64_t)(*n_dense_p) * nq;
   for (uint64_t item = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += n_warps) {
+    uint32_t n_hist = 0;  // entries of s_hist[.][threadIdx.x] in use (members of earlier groups); HIST + 1 = overflowed
     const uint32_t ci = (uint32_t)(item / nq);
     const uint64_t q = item - (uint64_t)ci * nq;
     const uint32_t c = dense_list[ci];
@@ -290,17 +295,29 @@ k_block_n(const uint32_t *__restrict__ dense_list, const uint32_t *__restrict__ 
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if (any4(and4(v[t], once))) {  // shares a site with a member of an earlier group: find out which
-            for (uint32_t x = 0; x < group_first; ++x) {
-              const uint32_t sx = __ldg(members + base + x);
-              if (!((word_of(sx) >> lane) & 1u)) continue;
-              const uint32_t cnt = popc4(and4(block_of(sx), v[t]));
-              if (cnt) atomicAdd(scratch_i + sq + (uint64_t)x * m + idx[t], cnt);
+            if (n_hist <= (uint32_t)HIST) {
+              for (uint32_t k = 0; k < n_hist; ++k) {
+                const uint32_t x = s_hist[k][threadIdx.x];
+                const uint32_t cnt = popc4(and4(block_of(__ldg(members + base + x)), v[t]));
+                if (cnt) atomicAdd(scratch_i + sq + (uint64_t)x * m + idx[t], cnt);
+              }
+            } else {  // history overflowed (a block where very many members have an N): walk over all earlier members
+              for (uint32_t x = 0; x < group_first; ++x) {
+                const uint32_t sx = __ldg(members + base + x);
+                if (!((word_of(sx) >> lane) & 1u)) continue;
+                const uint32_t cnt = popc4(and4(block_of(sx), v[t]));
+                if (cnt) atomicAdd(scratch_i + sq + (uint64_t)x * m + idx[t], cnt);
+              }
             }
           }
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           once.x |= v[t].x; once.y |= v[t].y; once.z |= v[t].z; once.w |= v[t].w;
+          if (idx[t] != 0xFFFFFFFFu) {
+            if (n_hist < (uint32_t)HIST) s_hist[n_hist][threadIdx.x] = (uint16_t)idx[t];
+            n_hist = min(n_hist + 1u, (uint32_t)HIST + 1u);
+          }
         }
       }
     }

@@ -200,6 +200,7 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
     for (uint64_t p : plan.rb_pairs) my_pairs += p;
     g_stats.n_pairs = my_pairs;
     unsigned long long nc = 0;
+    uint32_t words_used = 0;
     // windows of 4, 8, 16, 64 local words (any prefix of the slab's words gives a lower bound of d), widened while more
     // than 4 % of this rank's pairs survive; Wp is a multiple of KC. Kernel choice as in sweep_device.
     const uint32_t first = first_window(o.dist);
@@ -240,10 +241,31 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
       g_stats.swept_wordpairs += my_pairs * words;
       TRACS_CK(cudaMemcpyAsync(&nc, counter.p, sizeof nc, cudaMemcpyDeviceToHost, st));
       TRACS_CK(cudaStreamSynchronize(st));
+      words_used = words;
       if ((nc <= CAND_CAP && nc * 25 <= my_pairs) || words >= std::min<uint32_t>(PREFILTER_WORDS, g.Wp)) break;
     }
     if (nc > CAND_CAP)
       throw std::runtime_error("site-sharded sweep: the prefilter left too many candidate pairs; use the single-GPU / tile-sharded path");
+    if (nc && words_used < 16 && g.Wp > words_used) {
+      // narrow window: trim this rank's candidates over the next local words (k_cand_trim), so that the few unrelated
+      // pairs it let through do not bridge clusters in the candidate graph
+      T.start();
+      const uint32_t extra = std::min<uint32_t>(g.Wp - words_used, 32 - words_used);
+      DevBuf<uint8_t> flags(nc);
+      DevBuf<uint64_t> n_sel(1);
+      k_cand_trim<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(keys.p, dv.p, nc, g.planesT.p, g.Wp, words_used, extra, o.dist, flags.p);
+      size_t tb = 0;
+      cub::DeviceSelect::Flagged(nullptr, tb, keys.p, flags.p, keys2.p, n_sel.p, (int64_t)nc, st);
+      DevBuf<uint8_t> tmp(tb);
+      cub::DeviceSelect::Flagged(tmp.p, tb, keys.p, flags.p, keys2.p, n_sel.p, (int64_t)nc, st);
+      uint64_t kept = 0;
+      TRACS_CK(cudaMemcpyAsync(&kept, n_sel.p, 8, cudaMemcpyDeviceToHost, st));
+      TRACS_CK(cudaStreamSynchronize(st));
+      std::swap(keys.p, keys2.p);
+      g_stats.kernel_launches += 3;
+      g_stats.ms_refine += T.stop();
+      nc = kept;
+    }
     g_stats.n_candidates = nc;
     if (nc) {
       T.start();

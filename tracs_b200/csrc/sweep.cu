@@ -935,6 +935,30 @@ k_refine(const uint64_t *__restrict__ ckeys, const uint32_t *__restrict__ cdvals
   }
 }
 
+// Second, per-candidate prefilter after a NARROW tile window (4 or 8 words): one thread continues each candidate over
+// the next `extra` words of the sample-major planes and drops it once the partial distance passes `dist`. A narrow
+// window lets a few unrelated pairs through; left in, they would bridge clusters into large, sparse components of
+// the candidate graph (pairs.inl evaluates dense components as blocks). flags[e] = keep.
+__global__ void __launch_bounds__(256)
+k_cand_trim(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ dvals, uint64_t n_cand, const uint4 *__restrict__ planesT,
+            uint32_t Wp, uint32_t w0, uint32_t extra, int32_t dist, uint8_t *__restrict__ flags) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_cand) return;
+  const uint64_t k = keys[e];
+  const uint4 *ri = planesT + (k >> 32) * Wp + w0, *rj = planesT + (k & 0xFFFFFFFFull) * Wp + w0;
+  uint32_t d = dvals[e];
+  for (uint32_t w = 0; w < extra && (int32_t)d <= dist; w += 4) {
+#pragma unroll
+    for (uint32_t q = 0; q < 4; ++q) {
+      if (w + q < extra) {
+        const uint4 x = __ldg(ri + w + q), y = __ldg(rj + w + q);
+        d += __popc(~((x.x & y.x) | (x.y & y.y) | (x.z & y.z) | (x.w & y.w)));
+      }
+    }
+  }
+  flags[e] = (int32_t)d <= dist ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // K4: recombination filter for emitted edges (filter=True). Restates src/pairsnp.hpp:251-318:
 //   p = d / L; half-window h = clamp(int(1/p/2 + 1), 50, 5000); for every SNP of the pair, count the
@@ -1635,8 +1659,30 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
         S.ms_sweep += T.stop();
         S.n_tiles += n_tiles;
         S.swept_wordpairs += units[b].pairs * pw;
-        const unsigned long long n_cand = read_counter();
+        unsigned long long n_cand = read_counter();
         TRACS_CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+        if (n_cand && n_cand <= cap && n_cand * 25 <= units[b].pairs && pw < 16 && Wp > pw) {
+          // narrow window: trim the candidates over the next words, one thread each (k_cand_trim)
+          T.start();
+          const uint32_t extra = std::min<uint32_t>(Wp - pw, 32 - pw);
+          DevBuf<uint8_t> flags(n_cand);
+          DevBuf<uint64_t> n_sel(1);
+          k_cand_trim<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(keys.p, dv.p, n_cand, planesT.p, Wp, pw, extra, o.dist, flags.p);
+          size_t tb = 0;
+          cub::DeviceSelect::Flagged(nullptr, tb, keys.p, flags.p, keys2.p, n_sel.p, (int64_t)n_cand, st);
+          if (tb > sort_tmp_bytes) throw std::runtime_error("internal error: select scratch too small");
+          cub::DeviceSelect::Flagged(sort_tmp.p, tb, keys.p, flags.p, keys2.p, n_sel.p, (int64_t)n_cand, st);
+          cub::DeviceSelect::Flagged(sort_tmp.p, tb, dv.p, flags.p, dv2.p, n_sel.p, (int64_t)n_cand, st);
+          uint64_t kept = 0;
+          TRACS_CK(cudaMemcpyAsync(&kept, n_sel.p, 8, cudaMemcpyDeviceToHost, st));
+          TRACS_CK(cudaStreamSynchronize(st));
+          std::swap(keys.p, keys2.p);
+          std::swap(dv.p, dv2.p);
+          a.keys = keys.p; a.dvals = dv.p;
+          S.kernel_launches += 5;
+          S.ms_refine += T.stop();
+          n_cand = kept;
+        }
         if (n_cand <= cap && n_cand * 25 <= units[b].pairs) {  // <= 4 % survive: per-pair refinement is cheaper than tiles
           refined = true;
           S.n_candidates += n_cand;
