@@ -119,12 +119,19 @@ template <int MODE>
 __global__ void __launch_bounds__(BD_THREADS, 2)
 k_block_d(const uint2 *__restrict__ tasks, const uint32_t *__restrict__ task_off, uint32_t n, const uint32_t *__restrict__ members,
           const uint32_t *__restrict__ comp_start, const uint32_t *__restrict__ size, const uint64_t *__restrict__ sq_off,
-          const uint4 *__restrict__ planesT, uint64_t Wp /* uint4 per row */, uint32_t one, uint32_t *__restrict__ scratch_d) {
+          const uint4 *__restrict__ planesT, uint64_t Wp /* uint4 per row */, uint32_t one, uint32_t ksplit,
+          uint32_t *__restrict__ scratch_d) {
   __shared__ __align__(16) uint4 sm[2][2][PP_KC * 64];  // [stage][side][kk * 64 + slot]: 32 KB
   const uint32_t tid = threadIdx.x;
   const uint32_t n_tasks = task_off[n];
-  const uint32_t nchunks = (uint32_t)(Wp / PP_KC);
-  for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+  const uint32_t nchunks_all = (uint32_t)(Wp / PP_KC);
+  // ksplit > 1 (MODE 1 only): the row is cut into `ksplit` slices handled by different CTAs that add their counts up
+  // with atomics -- a handful of components over very long rows would otherwise keep only a handful of SMs busy
+  for (uint32_t vt = blockIdx.x; vt < n_tasks * ksplit; vt += gridDim.x) {
+    const uint32_t task = vt / ksplit, slice = vt - task * ksplit;
+    const uint32_t ch_lo = (uint32_t)((uint64_t)nchunks_all * slice / ksplit), ch_hi = (uint32_t)((uint64_t)nchunks_all * (slice + 1) / ksplit);
+    const uint32_t nchunks = ch_hi - ch_lo;
+    if (nchunks == 0) continue;
     const uint2 t = tasks[task];
     const uint32_t c = t.x, br = t.y >> 16, bc = t.y & 0xFFFFu;
     const uint32_t m = size[c], base = comp_start[c];
@@ -139,8 +146,8 @@ k_block_d(const uint2 *__restrict__ tasks, const uint32_t *__restrict__ task_off
     for (int k = 0; k < 2; ++k) {
       const uint32_t idx = tid + 256u * k, row = idx >> 3, kk = idx & 7u;
       dst[k] = kk * 64 + pp_slot(row);
-      srcA[k] = row < nr ? planesT + (size_t)members[base + r0 + row] * Wp + kk : nullptr;
-      srcB[k] = (!diag && row < nc) ? planesT + (size_t)members[base + c0 + row] * Wp + kk : nullptr;
+      srcA[k] = row < nr ? planesT + (size_t)members[base + r0 + row] * Wp + kk + (size_t)ch_lo * PP_KC : nullptr;
+      srcB[k] = (!diag && row < nc) ? planesT + (size_t)members[base + c0 + row] * Wp + kk + (size_t)ch_lo * PP_KC : nullptr;
     }
     auto stage = [&](uint32_t ch, uint32_t s) {
 #pragma unroll
@@ -215,7 +222,13 @@ k_block_d(const uint2 *__restrict__ tasks, const uint32_t *__restrict__ task_off
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t b = c0 + 4 * tx + j;
-          if (a < b && b < m) scratch_d[sq + (uint64_t)a * m + b] = MODE == 0 ? total_bits - acc[i][j] : acc[i][j];
+          if (a < b && b < m) {
+            if (MODE == 1 && ksplit > 1) {
+              if (acc[i][j]) atomicAdd(scratch_d + sq + (uint64_t)a * m + b, acc[i][j]);
+            } else {
+              scratch_d[sq + (uint64_t)a * m + b] = MODE == 0 ? total_bits - acc[i][j] : acc[i][j];
+            }
+          }
         }
       }
     }
@@ -447,7 +460,7 @@ static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const unsigned bgrid = (unsigned)std::min<uint64_t>(task_cap, (uint64_t)n_sm * 16);
-  k_block_d<0><<<bgrid, BD_THREADS, 0, st>>>(tasks.p, task_off.p, n, members.p, comp_start.p, size.p, sq_off.p, g.planesT.p, g.Wp, 1u,
+  k_block_d<0><<<bgrid, BD_THREADS, 0, st>>>(tasks.p, task_off.p, n, members.p, comp_start.p, size.p, sq_off.p, g.planesT.p, g.Wp, 1u, 1u,
                                            scratch_d.p);
   if (u_out) {
     // N intersections: summary-guided (k_block_n) while most 128-site blocks are free of N; a dense AND + POPC
@@ -457,11 +470,13 @@ static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint
     bool dense_n = 1.0 - pow(1.0 - std::min(1.0, p_n), 128.0) > 0.35;
     if (nmode && !strcmp(nmode, "dense")) dense_n = true;
     if (nmode && !strcmp(nmode, "sparse")) dense_n = false;
+    TRACS_CK(cudaMemsetAsync(scratch_i.p, 0, sq_cap * sizeof(uint32_t), st));
     if (dense_n) {
-      k_block_d<1><<<bgrid, BD_THREADS, 0, st>>>(tasks.p, task_off.p, n, members.p, comp_start.p, size.p, sq_off.p,
-                                               reinterpret_cast<const uint4 *>(g.nplane.p), g.npitch / 4, 1u, scratch_i.p);
+      const uint32_t ksplit = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, g.npitch / 4 / PP_KC / 64));  // >= 64 chunks per slice
+      k_block_d<1><<<(unsigned)std::min<uint64_t>(task_cap * ksplit, (uint64_t)n_sm * 16), BD_THREADS, 0, st>>>(
+          tasks.p, task_off.p, n, members.p, comp_start.p, size.p, sq_off.p, reinterpret_cast<const uint4 *>(g.nplane.p), g.npitch / 4, 1u,
+          ksplit, scratch_i.p);
     } else {
-      TRACS_CK(cudaMemsetAsync(scratch_i.p, 0, sq_cap * sizeof(uint32_t), st));
       k_block_n<<<n_sm * 8, 256, 0, st>>>(dense_list.p, n_dense.p, members.p, comp_start.p, size.p, sq_off.p, g.nplane.p, g.npitch, g.nsum.p,
                                         g.spitch, scratch_i.p);
     }

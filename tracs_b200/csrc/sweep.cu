@@ -1346,7 +1346,7 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   // pack of all other samples store those sites' masks on the way. TRACS_INGEST=split / =early overrides the rule.
   const char *mode_env = getenv("TRACS_INGEST");
   const uint64_t n_first = PACK_SCHUNK;
-  bool early = L >= (1u << 16) && n >= 8 * n_first && L < (1ull << 31);
+  bool early = L >= (1u << 16) && n >= 4 * n_first && L < (1ull << 31);
   if (mode_env && !strcmp(mode_env, "split")) early = false;
   if (mode_env && !strcmp(mode_env, "early")) early = L > 0 && n > n_first && L < (1ull << 31);
   DevBuf<uint32_t> elist;
