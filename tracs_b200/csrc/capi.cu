@@ -44,8 +44,11 @@ void *dev_cache_alloc(size_t bytes) {
   DevCache &dc = dev_cache();
   {
     std::lock_guard<std::mutex> g(dc.mu);
-    // smallest idle block on this device that fits without wasting more than a quarter of it
-    for (auto it = dc.idle.lower_bound(want); it != dc.idle.end() && it->first <= want + want / 4 + DEV_GRANULE; ++it) {
+    // smallest idle block on this device that fits without wasting more than a quarter of it (multi-GB requests) or
+    // more than the request itself (smaller ones: a run over alignments of different shapes, one MSA per reference,
+    // would otherwise miss the cache on every call and pay a cudaMalloc per buffer)
+    const size_t slack = want >= ((size_t)4 << 30) ? want / 4 : want;
+    for (auto it = dc.idle.lower_bound(want); it != dc.idle.end() && it->first <= want + slack + DEV_GRANULE; ++it) {
       if (it->second.second != dev) continue;
       void *p = it->second.first;
       dc.live[p] = {it->first, dev};
