@@ -280,10 +280,12 @@ def hbm_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
 
 
-def kernel_traffic():
+def kernel_traffic(config=None):
+    """DRAM bytes per launch from the committed ncu captures (profiles/kernel_traffic.json), keyed by the config whose
+    launch was captured: a figure is only attached to a launch of the same shape."""
     p = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     try:
-        return json.load(open(p))
+        return json.load(open(p)).get(config or "", {})
     except Exception:
         return {}
 
@@ -357,12 +359,12 @@ def spot_checks(inp, res, dist, n_check=10, seed=0):
 # ------------------------------------------------------------------------------------------------
 # rooflines
 # ------------------------------------------------------------------------------------------------
-def rooflines(tracs_b200, w, stats, peak, n_rows, L_slab, tc_peak):
+def rooflines(tracs_b200, w, stats, peak, n_rows, L_slab, tc_peak, config=None, whole=True):
     """Per-kernel roofline entries from the library's stage timers (CUDA events on the call's stream)."""
     def avg(k):
         return float(np.mean([s[k] for s in stats]))
     hbm, hbm_src = hbm_peak()
-    traffic = kernel_traffic()
+    traffic = kernel_traffic(config) if whole else {}   # per-launch DRAM bytes only apply to the whole-alignment launch
     peak_wp = min(peak["lop3_per_s"] / 4.0, peak["popc_per_s"])
     packed = w["fmt"] == "packed"
     npitch_words = max(32, ((L_slab + 31) // 32 + 31) // 32 * 32)
@@ -376,26 +378,33 @@ def rooflines(tracs_b200, w, stats, peak, n_rows, L_slab, tc_peak):
     pack_bytes = in_bytes + n_main * npitch_words * 4 + n_main * (npitch_words // 32) + n_main * n_early
     ms_main = avg("ms_pack_main")
     roof_pack = {"bound": "hbm", "kernel": pack_kernel, "achieved": pack_bytes / (ms_main * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                 "frac": pack_bytes / (ms_main * 1e-3) / 1e9 / hbm, "traffic": traffic.get(pack_kernel + "_dram_bytes_per_launch"),
+                 "frac": pack_bytes / (ms_main * 1e-3) / 1e9 / hbm, "traffic": traffic.get(pack_kernel),
                  "ms_per_launch": ms_main, "algorithmic_bytes": pack_bytes, "samples_in_launch": n_main, "early_sites": n_early,
                  "peak_source": hbm_src}
     wp = avg("swept_wordpairs")
     ms_sw = avg("ms_sweep")
     pf_words = int(round(wp / max(1.0, avg("n_pairs"))))
-    what = "prefilter launch (first %d words of every pair)" % pf_words if avg("n_candidates") > 0 or avg("ms_refine") > 0 else "full-length sweep"
+    prefiltered = (avg("n_candidates") > 0 or avg("ms_refine") > 0) and pf_words < int(round(avg("n_words")))
+    what = "prefilter launch (first %d words of every pair)" % pf_words if prefiltered else "full-length sweep (%d words)" % pf_words
     if avg("tc_sweep") > 0.5:
-        roof_sweep = tc_roof(wp, ms_sw, what, tc_peak, peak_wp)
+        roof_sweep = tc_roof(wp, ms_sw, what, tc_peak, peak_wp, code=int(round(avg("tc_sweep"))))
     else:
         roof_sweep = int_roof(wp, ms_sw, what, peak, traffic)
     return roof_pack, roof_sweep, pack_kernel
 
 
-def tc_roof(wordpairs, ms, what, tc_peak, peak_wp):
-    macs = wordpairs * 32 * 4          # algorithmic: one-hot K = 4 per site; the kernel executes K = 5 (N column)
+TC_KERNELS = {1: "k_sweep_tc", 2: "k_sweep_tc2", 3: "k_sweep_tc3"}
+
+
+def tc_roof(wordpairs, ms, what, tc_peak, peak_wp, code=33):
+    """`code` = tracs_stats_t.tc_sweep: 10 * kernel generation + int8 operand planes executed per site."""
+    macs = wordpairs * 32 * 4          # algorithmic: one-hot K = 4 per site (SURVEY 8d)
+    gen, planes = divmod(int(code), 10)
+    kernel = TC_KERNELS.get(gen, "k_sweep_tc") + ("<%d>" % planes if gen >= 2 else "")
     pk = tc_peak["tops"] if tc_peak else 4500.0
-    return {"bound": "tensor", "kernel": "k_sweep_tc", "what": what, "achieved": 2 * macs / (ms * 1e-3) / 1e12, "peak": pk,
+    return {"bound": "tensor", "kernel": kernel, "what": what, "achieved": 2 * macs / (ms * 1e-3) / 1e12, "peak": pk,
             "unit": "TOP/s", "frac": 2 * macs / (ms * 1e-3) / 1e12 / pk, "traffic": None, "ms_per_launch": ms,
-            "executed_tops": 2 * macs * 1.25 / (ms * 1e-3) / 1e12,
+            "executed_planes_per_site": planes, "executed_tops": 2 * macs * (planes / 4.0) / (ms * 1e-3) / 1e12,
             "peak_source": (tc_peak["source"] if tc_peak else "NOMINAL dense int8 (4.5 POP/s)"),
             "equivalent_int_pipe_frac": (wordpairs / (ms * 1e-3)) / peak_wp}
 
@@ -404,8 +413,7 @@ def int_roof(wordpairs, ms, what, peak, traffic):
     peak_wp = min(peak["lop3_per_s"] / 4.0, peak["popc_per_s"])
     return {"bound": "int_pipe", "kernel": "k_sweep", "what": what, "achieved": wordpairs * 6 / (ms * 1e-3) / 1e9,
             "peak": peak_wp * 6 / 1e9, "unit": "Ginstr/s", "frac": (wordpairs * 6 / (ms * 1e-3)) / (peak_wp * 6),
-            "traffic": traffic.get("k_sweep_full_length_dram_bytes_per_launch") if what.startswith("full") else
-            traffic.get("k_sweep_prefilter_dram_bytes_per_launch"),
+            "traffic": traffic.get("k_sweep_full_length") if what.startswith("full") else traffic.get("k_sweep_prefilter"),
             "achieved_wordpairs_per_s": wordpairs / (ms * 1e-3), "ms_per_launch": ms,
             "peak_source": "measured in this run (tracs_int_peak: register-resident LOP3 and POPC loops; a word-pair needs "
                            "4 LOP3 on the 64-lane ALU pipe and 1 POPC on the 16-lane XU pipe => min(lop3/4, popc) word-pairs/s)",
@@ -547,7 +555,7 @@ def main():
     if rank == 0:
         n_edges = len(res["rows"])
         launches = int(sum(s["kernel_launches"] for s in stats))
-        roof_pack, roof_sweep, pack_kernel = rooflines(tracs_b200, w, stats, peak, n, inp.Ls, tc_peak)
+        roof_pack, roof_sweep, pack_kernel = rooflines(tracs_b200, w, stats, peak, n, inp.Ls, tc_peak, config=args.config if not (args.n or args.L) else None, whole=(world == 1))
         keys = ("ms_pack", "ms_pack_main", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_d2h", "ms_total",
                 "ms_finish")
         stages = {k: avg(k) for k in keys}
@@ -590,8 +598,9 @@ def main():
                     s2 = tracs_b200.last_stats()
                     rf = (tc_roof(s2["swept_wordpairs"], s2["ms_sweep"], "full-length sweep, tcgen05.mma kind::i8, operands expanded from the "
                                   "bit-planes in shared memory, int32 accumulators in TMEM", tc_peak,
-                                  min(peak["lop3_per_s"] / 4.0, peak["popc_per_s"])) if variant == "tc" else
-                          int_roof(s2["swept_wordpairs"], s2["ms_sweep"], "full-length sweep (prefilter disabled)", peak, kernel_traffic()))
+                                  min(peak["lop3_per_s"] / 4.0, peak["popc_per_s"]), code=int(round(s2["tc_sweep"]))) if variant == "tc" else
+                          int_roof(s2["swept_wordpairs"], s2["ms_sweep"], "full-length sweep (prefilter disabled)", peak,
+                                   kernel_traffic(args.config if not (args.n or args.L) else None)))
                     rf["whole_step_ms"] = 1e3 * t_full
                     rf["edges_equal_default_path"] = bool(all(np.array_equal(r2[k], res[k]) for k in ("rows", "cols", "dist", "ncomp")))
                     kernels[nm] = rf

@@ -75,7 +75,8 @@ typedef struct tracs_stats {
   float ms_total;            /* device time of the whole call (events on the call's stream) */
   float ms_d2h;              /* edge columns device -> host                                  */
   float ms_filter;           /* recombination filter (K4), only when filter != 0             */
-  float tc_sweep;            /* 1 if the tile sweep launches ran on the tensor cores (k_sweep_tc) */
+  float tc_sweep;            /* 0: LOP3/POPC tile kernel; else 10 * generation + int8 operand planes executed per site:
+                                15 = k_sweep_tc, 23 / 24 = k_sweep_tc2<3|4>, 33 / 34 = k_sweep_tc3<3|4> */
   float ms_pack_main;        /* the main pack launch alone: k_pack_x over samples 256.. (early extraction) or k_pack over all */
 } tracs_stats_t;
 

@@ -430,11 +430,12 @@ def test_tensor_core_sweep_v2_planes(oracle_mod, monkeypatch, n, L, dist, p_N):
     s = synth.generate(n, L, p_var=0.08, n_clusters=5, mu=4, p_N=p_N, p_amb=0.0, seed=n + L, lowercase=0.05, gaps=0 if p_N == 0 else 2)
     orc = oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=4)
     res = tracs_b200.pairsnp_matrix(s, dist=dist, full_sweep="tc")      # k_sweep_tc3: 128 x 512 super-tiles
-    assert tracs_b200.last_stats()["tc_sweep"] == 1.0
+    assert tracs_b200.last_stats()["tc_sweep"] in (33.0, 34.0)          # generation 3, three or four operand planes
     _cmp(res, orc)
-    for v in ("v2", "v1"):                                               # 128 x 128 tiles; the round-1 kernel
+    for v, codes in (("v2", (23.0, 24.0)), ("v1", (15.0,))):             # 128 x 128 tiles; the round-1 kernel
         monkeypatch.setenv("TRACS_TC", v)
         _cmp(tracs_b200.pairsnp_matrix(s, dist=dist, full_sweep="tc"), orc)
+        assert tracs_b200.last_stats()["tc_sweep"] in codes
     monkeypatch.delenv("TRACS_TC")
     for n1 in (n // 3, n - 1):                                           # query x db ranges cut super-tiles short
         _cmp(tracs_b200.pairsnp_matrix(s, dist=dist, i_end=n1, j_start=n1, full_sweep="tc"),

@@ -1197,8 +1197,9 @@ static void launch_tile_sweep(const SweepArgs &a_in, bool use_tc, cudaStream_t s
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (a.n_tiles == 0) return;
-  g_stats.tc_sweep = use_tc ? 1.0f : 0.0f;
   const char *tcv = getenv("TRACS_TC");  // "v1": the round-1 kernel (five one-hot planes), kept for comparison
+  // which kernel ran: 10 * generation + operand planes executed (15 = k_sweep_tc, 23/24 = k_sweep_tc2, 33/34 = k_sweep_tc3)
+  g_stats.tc_sweep = !use_tc ? 0.0f : (tcv && !strcmp(tcv, "v1")) ? 15.0f : ((tcv && !strcmp(tcv, "v2")) ? 20.0f : 30.0f) + (has_n ? 4.0f : 3.0f);
   DevBuf<uint32_t> ncnt;
   if (use_tc && tcv && !strcmp(tcv, "v1")) {
     k_sweep_tc<<<(unsigned)std::min<uint64_t>(a.n_tiles, (uint64_t)n_sm), TC_THREADS, TC_SMEM, st>>>(a);
