@@ -375,12 +375,21 @@ def rooflines(tracs_b200, w, stats, peak, n_rows, L_slab, tc_peak, config=None, 
     # algorithmic bytes: per base 1 B (ASCII) or 1/2 B (packed) read + 1/8 B N-plane write (+ summary byte per
     # 1024 sites); the extracting variant also writes one byte per (sample, early site)
     in_bytes = n_main * (L_slab // 2 if packed else L_slab)
-    pack_bytes = in_bytes + n_main * npitch_words * 4 + n_main * (npitch_words // 32) + n_main * n_early
+    nplane_bytes = n_main * npitch_words * 4
+    sparse_n = avg("sparse_nplane") > 0.5
+    if sparse_n:
+        # sparse N: only the 128-site blocks that hold an N are algorithmic output (16 B each; the kernel stores whole 32-byte
+        # sectors). Expected share from the generator: i.i.d. N at p_N plus `gaps` runs of L/1000 sites per sample
+        blocks = max(1, (L_slab + 127) // 128)
+        f = 1.0 - (1.0 - w["p_N"]) ** 128
+        f = min(1.0, f + w.get("gaps", 0) * ((w["L"] // 1000) / 128.0 + 1.0) / blocks)
+        nplane_bytes = int(nplane_bytes * f)
+    pack_bytes = in_bytes + nplane_bytes + n_main * (npitch_words // 32) + n_main * n_early
     ms_main = avg("ms_pack_main")
     roof_pack = {"bound": "hbm", "kernel": pack_kernel, "achieved": pack_bytes / (ms_main * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                  "frac": pack_bytes / (ms_main * 1e-3) / 1e9 / hbm, "traffic": traffic.get(pack_kernel),
                  "ms_per_launch": ms_main, "algorithmic_bytes": pack_bytes, "samples_in_launch": n_main, "early_sites": n_early,
-                 "peak_source": hbm_src}
+                 "n_plane": "sparse stores (blocks that hold an N)" if sparse_n else "every word stored", "peak_source": hbm_src}
     wp = avg("swept_wordpairs")
     ms_sw = avg("ms_sweep")
     pf_words = int(round(wp / max(1.0, avg("n_pairs"))))

@@ -78,6 +78,8 @@ typedef struct tracs_stats {
   float tc_sweep;            /* 0: LOP3/POPC tile kernel; else 10 * generation + int8 operand planes executed per site:
                                 15 = k_sweep_tc, 23 / 24 = k_sweep_tc2<3|4>, 33 / 34 = k_sweep_tc3<3|4> */
   float ms_pack_main;        /* the main pack launch alone: k_pack_x over samples 256.. (early extraction) or k_pack over all */
+  float sparse_nplane;       /* 1: sparse N (first-chunk estimate): the main ingest launch stored only the N-plane sectors that hold an N */
+  float reserved0;
 } tracs_stats_t;
 
 /* Options shared by the matrix-input entry points. Zero-initialise, then set. */

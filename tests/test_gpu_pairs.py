@@ -105,3 +105,48 @@ def test_dense_and_sparse_N_intersections_agree(oracle_mod, monkeypatch, p_N):
         assert tracs_b200.last_stats()["ms_refine"] > 0
         _cmp(res, orc)
     assert len(orc[0]) > 500
+
+
+@pytest.mark.parametrize("n,L,p_var,p_N,dist,expect_refine", [(600, 150_001, 0.06, 0.002, 25, True), (1100, 140_000, 0.06, 0.01, 25, True),
+                                                              (400, 99_999, 0.10, 0.0, 20, True), (520, 66_030, 0.06, 0.002, 2000, False)])
+def test_sparse_nplane_stores_match_oracle(oracle_mod, monkeypatch, n, L, p_var, p_N, dist, expect_refine):
+    """Sparse N on the early-extraction ingest: the main launch stores only the 256-site groups of the N bit-plane that hold
+    an N (pack_emit_n<true>); the rest of the buffer is stale and must never be read. The buffer is first filled with
+    ones by an N-only call of the same shape, so that a consumer that strays off the block summaries shows up.
+    Against the oracle and against full stores (TRACS_NPLANE=always); per-candidate kernel forced as well; dist = 2000
+    leaves the prefilter out, so the per-edge tail (k_ncomp) reads the sparsely stored plane."""
+    s = synth.generate(n, L, p_var=p_var, n_clusters=max(2, n // 12), mu=4, p_N=p_N, p_amb=0.01, seed=n + 11, gaps=3)
+    orc = oracle_mod.pairsnp_ascii(s, dist=dist, n_threads=8)
+    poison = np.full_like(s, ord("N"))
+    poison[:, ::97] = ord("A")
+    monkeypatch.setenv("TRACS_INGEST", "early")
+    for mode, sparse in (("sparse", 1.0), ("always", 0.0)):
+        monkeypatch.setenv("TRACS_NPLANE", "always")
+        tracs_b200.pairsnp_matrix(poison, dist=0)        # leaves an all-ones N-plane in the cached buffer
+        monkeypatch.setenv("TRACS_NPLANE", mode)
+        res = tracs_b200.pairsnp_matrix(s, dist=dist)
+        st = tracs_b200.last_stats()
+        assert st["sparse_nplane"] == sparse and st["n_early_sites"] > 0
+        if expect_refine:
+            assert st["ms_refine"] > 0, "filter-and-refine (component blocks) is the path under test"
+        _cmp(res, orc)
+        monkeypatch.setenv("TRACS_PAIRS", "sparse")
+        _cmp(tracs_b200.pairsnp_matrix(s, dist=dist), orc)
+        monkeypatch.delenv("TRACS_PAIRS")
+    monkeypatch.delenv("TRACS_NPLANE")
+    frac_n = float(np.mean((s == ord("N")) | (s == ord("-"))))
+    res = tracs_b200.pairsnp_matrix(s, dist=dist)       # the density rule on the first chunk decides
+    assert tracs_b200.last_stats()["sparse_nplane"] == (1.0 if 1.0 - (1.0 - frac_n) ** 128 <= 0.30 else tracs_b200.last_stats()["sparse_nplane"])
+    _cmp(res, orc)
+
+
+def test_dense_N_keeps_whole_rows(oracle_mod, monkeypatch):
+    """N-rich packed input (BASELINE configs[3] shape): the first chunk shows dense N, every N-plane word is stored and the
+    dense contraction (k_block_d<1>) runs."""
+    s = synth.generate(700, 80_000, p_var=0.08, n_clusters=30, mu=4, p_N=0.3, p_amb=0.02, seed=5, gaps=2)
+    orc = oracle_mod.pairsnp_ascii(s, dist=12, n_threads=8)
+    monkeypatch.setenv("TRACS_INGEST", "early")
+    res = tracs_b200.pairsnp_matrix(s, dist=12)
+    st = tracs_b200.last_stats()
+    assert st["sparse_nplane"] == 0.0 and st["n_early_sites"] > 0
+    _cmp(res, orc)

@@ -25,7 +25,7 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("n_samples", "seq_length", "n_variable_sites", "n_words", "n_tiles", "n_pairs",
                                           "n_edges", "kernel_launches", "h2d_bytes", "d2h_bytes", "n_candidates",
                                           "swept_wordpairs", "n_early_sites")] + \
-               [(k, C.c_float) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_total", "ms_d2h", "ms_filter", "tc_sweep", "ms_pack_main")]
+               [(k, C.c_float) for k in ("ms_pack", "ms_compact", "ms_sweep", "ms_refine", "ms_sort", "ms_ncomp", "ms_trans", "ms_total", "ms_d2h", "ms_filter", "tc_sweep", "ms_pack_main", "sparse_nplane", "reserved0")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -175,7 +175,9 @@ def take_edges(e, as_lists=False, names=True, copy=True):
     else:
         out._owner = _EdgeOwner(e)
     if out["filt"] is None and e_has_rows:
-        out["filt"] = np.zeros(n, np.uint64)   # filter off: the reference returns a vector of zeros (src/pairsnp.hpp:452)
+        # filter off: the reference returns a vector of zeros (src/pairsnp.hpp:452). A zero-stride read-only view: a real
+        # 8 B x E array costs 1.4 - 4 ms per C3 call (glibc hands back recycled heap that calloc has to clear)
+        out["filt"] = np.broadcast_to(np.uint64(0), (n,))
     if as_lists:
         for k in ("rows", "cols", "dist", "filt", "ncomp"):
             out[k] = out[k].tolist()

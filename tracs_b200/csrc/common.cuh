@@ -101,6 +101,45 @@ struct DevBuf {
   ~DevBuf() { release(); }
 };
 
+// One auxiliary stream per host thread and device (non-blocking: no implicit ordering with the legacy default stream
+// the entry points run on): side work that overlaps the main stream -- the likelihood table under the ingest, the
+// copies of finished edge columns under the compared-sites kernel. Ordering is by events only.
+inline cudaStream_t aux_stream() {
+  static thread_local cudaStream_t s[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!s[dev]) cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking);
+  return s[dev];
+}
+
+// Stage timers that do not stall the host: event pairs are recorded as the work is enqueued and read once at the end.
+struct DeferredTimers {
+  struct Item { cudaEvent_t a, b; float *acc; };
+  std::vector<Item> items;
+  cudaStream_t s;
+  explicit DeferredTimers(cudaStream_t st) : s(st) {}
+  void start(float *acc) {
+    Item it{nullptr, nullptr, acc};
+    cudaEventCreate(&it.a);
+    cudaEventCreate(&it.b);
+    cudaEventRecord(it.a, s);
+    items.push_back(it);
+  }
+  void stop() { cudaEventRecord(items.back().b, s); }
+  void resolve() {  // after the stream has been synchronised
+    for (Item &it : items) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, it.a, it.b) == cudaSuccess) *it.acc += ms;
+      else cudaGetLastError();  // unwinding after an error: the pair was never completed
+      cudaEventDestroy(it.a);
+      cudaEventDestroy(it.b);
+    }
+    items.clear();
+  }
+  ~DeferredTimers() { resolve(); }
+};
+
 struct Timer {
   cudaEvent_t a, b;
   cudaStream_t s;

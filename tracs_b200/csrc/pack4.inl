@@ -20,14 +20,11 @@ namespace tracs {
 constexpr int P4_BATCH = 8;   // samples per trip: 8 x 16 B in flight per thread
 constexpr int P4_ROUNDS = 3;  // extraction items per lane held in registers (a warp rarely lists more than 12 sites)
 
-// bit 4k of the result = nibble k of v is 1111
-__device__ __forceinline__ uint32_t nib_is_n(uint32_t v) {
-  uint32_t t = v & (v >> 1);
-  t &= (t >> 2);
-  return t & 0x11111111u;
-}
+// bit 4k + 3 of the result = nibble k of v is 1111: adding 1 to the low three bits carries into bit 3 iff they are all
+// set (three operations per register; the shift-and-AND form needs four, and this kernel's ALU pipe is two thirds busy)
+__device__ __forceinline__ uint32_t nib_is_n_hi(uint32_t v) { return ((v & 0x77777777u) + 0x11111111u) & v & 0x88888888u; }
 __device__ __forceinline__ uint32_t p4_isn(const uint4 &v) {
-  return nib_is_n(v.x) | (nib_is_n(v.y) << 1) | (nib_is_n(v.z) << 2) | (nib_is_n(v.w) << 3);
+  return (nib_is_n_hi(v.x) >> 3) | (nib_is_n_hi(v.y) >> 2) | (nib_is_n_hi(v.z) >> 1) | nib_is_n_hi(v.w);
 }
 // valid sites of a word, in this family's N-plane bit order
 __device__ __forceinline__ uint32_t p4_validp(uint32_t nvalid) {
@@ -74,7 +71,7 @@ k_encode(const uint8_t *__restrict__ ascii, uint64_t rows, uint64_t L, uint64_t 
   __stcs(reinterpret_cast<uint4 *>(nib + s * pitch4 + w * 16), o);
 }
 
-template <bool EXTRACT>
+template <bool EXTRACT, bool SPARSE_N = false>
 __global__ void __launch_bounds__(PACK_THREADS, 3)
 k_pack4(const uint8_t *__restrict__ nib, uint64_t s_begin, uint64_t s_end, uint64_t L, uint64_t pitch4, uint32_t *__restrict__ colmask,
         uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/,
@@ -155,7 +152,7 @@ k_pack4(const uint8_t *__restrict__ nib, uint64_t s_begin, uint64_t s_end, uint6
         if (EXTRACT && nE) *reinterpret_cast<uint4 *>(mine + t * 512) = va[t];  // warp-uniform condition
         if (FULL || (uint32_t)t < rows) {
           acc.x &= va[t].x; acc.y &= va[t].y; acc.z &= va[t].z; acc.w &= va[t].w;
-          pack_emit_n(p4_isn(va[t]) & validp, np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, lane);
+          pack_emit_n<SPARSE_N>(p4_isn(va[t]) & validp, np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, lane);
         }
       }
       if (EXTRACT && nE) {  // warp-uniform

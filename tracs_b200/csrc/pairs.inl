@@ -349,7 +349,7 @@ __global__ void k_pairs_gather(const uint64_t *__restrict__ keys, uint64_t E, co
   const uint32_t c = root[i];
   if (!dense[c]) return;
   const uint64_t idx = sq_off[c] + (uint64_t)rank[i] * size[c] + rank[j];  // i < j and members are in sample order: rank[i] < rank[j]
-  d_out[e] = scratch_d[idx];
+  if (d_out) d_out[e] = scratch_d[idx];
   if (u_out) u_out[e] = ncount[i] + ncount[j] - scratch_i[idx];
 }
 
@@ -375,10 +375,12 @@ k_pairs_sparse(const uint64_t *__restrict__ keys, uint64_t n_keys, const uint32_
   const uint64_t i = k >> 32, j = k & 0xFFFFFFFFull;
   const uint4 *ri = planesT + i * Wp, *rj = planesT + j * Wp;
   uint32_t mism = 0;
+  if (d_out) {
 #pragma unroll 4
-  for (uint32_t w = lane; w < Wp; w += 32) {
-    const uint4 x = __ldg(ri + w), y = __ldg(rj + w);
-    mism += __popc(~((x.x & y.x) | (x.y & y.y) | (x.z & y.z) | (x.w & y.w)));
+    for (uint32_t w = lane; w < Wp; w += 32) {
+      const uint4 x = __ldg(ri + w), y = __ldg(rj + w);
+      mism += __popc(~((x.x & y.x) | (x.y & y.y) | (x.z & y.z) | (x.w & y.w)));
+    }
   }
   uint32_t inter = 0;
   if (u_out) {
@@ -402,67 +404,97 @@ k_pairs_sparse(const uint64_t *__restrict__ keys, uint64_t n_keys, const uint32_
     inter += __shfl_xor_sync(0xFFFFFFFFu, inter, o);
   }
   if (lane == 0) {
-    d_out[e] = mism;
+    if (d_out) d_out[e] = mism;
     if (u_out) u_out[e] = ncount[i] + ncount[j] - inter;
   }
   }
 }
 
 // keys: E candidate keys (i << 32 | j, i < j), any order, no duplicates. d_out[e] = mismatches of the pair over all
-// ingested words; u_out[e] (may be null) = |N_i u N_j| over the ingested sites. TRACS_PAIRS=sparse forces the
-// per-candidate kernel for everything (tests compare both).
-static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint32_t *d_out, uint32_t *u_out, cudaStream_t st) {
-  tracs_stats_t &S = g_stats;
-  if (E == 0) return;
-  const uint32_t n = (uint32_t)g.n;
-  const char *mode = getenv("TRACS_PAIRS");
-  const bool blocks = !(mode && !strcmp(mode, "sparse")) && E < (1ull << 31);
-  auto grid1 = [](uint64_t items) { return (unsigned)((items + 255) / 256); };
-  if (!blocks) {
-    k_pairs_sparse<<<grid1(E), 256, 0, st>>>(keys, E, nullptr, nullptr, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
-                                                g.ncount.p, d_out, u_out);
-    S.kernel_launches++;
+// ingested words; u_out[e] = |N_i u N_j| over the ingested sites. Two phases, so that a caller can hand the distances
+// on (threshold, likelihood, copies to the host) while the compared-sites part is still running: distances() first,
+// then unions(). TRACS_PAIRS=sparse forces the per-candidate kernel for everything (tests compare both).
+struct PairEval {
+  bool blocks = false;
+  uint32_t n = 0;
+  uint64_t sq_cap = 0, task_cap = 0;
+  int n_sm = 148;
+  DevBuf<uint32_t> parent, iota, size, ecnt, ntasks, task_off, dense_list, n_dense, sroot, members, comp_start, rank;
+  DevBuf<uint64_t> msq, sq_off;
+  DevBuf<uint8_t> dense, tmp;
+  DevBuf<uint2> tasks;
+  DevBuf<uint32_t> scratch_d, scratch_i;
+  static unsigned grid1(uint64_t items) { return (unsigned)((items + 255) / 256); }
+
+  void distances(const Ingested &g, const uint64_t *keys, uint64_t E, uint32_t *d_out, cudaStream_t st) {
+    tracs_stats_t &S = g_stats;
+    if (E == 0) return;
+    n = (uint32_t)g.n;
+    const char *mode = getenv("TRACS_PAIRS");
+    blocks = !(mode && !strcmp(mode, "sparse")) && E < (1ull << 31);
+    if (!blocks) {
+      k_pairs_sparse<<<grid1(E), 256, 0, st>>>(keys, E, nullptr, nullptr, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
+                                                  g.ncount.p, d_out, nullptr);
+      S.kernel_launches++;
+      TRACS_CK(cudaGetLastError());
+      return;
+    }
+    // ---- components of the candidate graph --------------------------------------------------------------------
+    parent.alloc(n); iota.alloc(n); size.alloc(n); ecnt.alloc(n); ntasks.alloc(n + 1); task_off.alloc(n + 1); dense_list.alloc(n);
+    n_dense.alloc(1); sroot.alloc(n); members.alloc(n); comp_start.alloc(n); rank.alloc(n);
+    msq.alloc(n + 1); sq_off.alloc(n + 1);
+    dense.alloc(n);
+    TRACS_CK(cudaMemsetAsync(size.p, 0, n * sizeof(uint32_t), st));
+    TRACS_CK(cudaMemsetAsync(ecnt.p, 0, n * sizeof(uint32_t), st));
+    TRACS_CK(cudaMemsetAsync(n_dense.p, 0, sizeof(uint32_t), st));
+    k_pp_init<<<grid1(n), 256, 0, st>>>(parent.p, iota.p, n);
+    k_pp_hook<<<grid1(E), 256, 0, st>>>(keys, E, parent.p);
+    k_pp_flatten<<<grid1(n), 256, 0, st>>>(parent.p, n, size.p);
+    k_pp_count<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, ecnt.p);
+    k_pp_decide<<<grid1((uint64_t)n + 1), 256, 0, st>>>(parent.p, size.p, ecnt.p, n, dense.p, ntasks.p, msq.p, dense_list.p, n_dense.p);
+    size_t tb1 = 0, tb2 = 0, tb3 = 0;
+    int end_bit = 1;
+    while ((1ull << end_bit) < n) end_bit++;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb1, ntasks.p, task_off.p, (int64_t)n + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, msq.p, sq_off.p, (int64_t)n + 1, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb3, parent.p, sroot.p, iota.p, members.p, (int64_t)n, 0, end_bit, st);
+    tmp.alloc(std::max(tb1, std::max(tb2, tb3)));
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb1, ntasks.p, task_off.p, (int64_t)n + 1, st);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb2, msq.p, sq_off.p, (int64_t)n + 1, st);
+    cub::DeviceRadixSort::SortPairs(tmp.p, tb3, parent.p, sroot.p, iota.p, members.p, (int64_t)n, 0, end_bit, st);  // stable: members stay in sample order
+    k_pp_heads<<<grid1(n), 256, 0, st>>>(sroot.p, n, comp_start.p);
+    k_pp_rank<<<grid1(n), 256, 0, st>>>(sroot.p, members.p, n, comp_start.p, rank.p);
+    // capacity bounds that need no round trip to the host: a dense component has m(m-1)/2 <= 4 x its candidates, so
+    // sum m^2 <= 8 E + n matrix entries, and (m/64 + 1)^2 block tasks
+    sq_cap = 8 * E + n + 16;
+    task_cap = E / 256 + 2ull * n + 16;
+    tasks.alloc(task_cap);
+    scratch_d.alloc(sq_cap);
+    k_pp_tasks<<<grid1(n), 256, 0, st>>>(ntasks.p, task_off.p, size.p, n, tasks.p);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned bgrid = (unsigned)std::min<uint64_t>(task_cap, (uint64_t)n_sm * 16);
+    k_block_d<0><<<bgrid, BD_THREADS, 0, st>>>(tasks.p, task_off.p, n, members.p, comp_start.p, size.p, sq_off.p, g.planesT.p, g.Wp, 1u, 1u,
+                                             scratch_d.p);
+    k_pairs_gather<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, rank.p, size.p, sq_off.p, scratch_d.p, nullptr, g.ncount.p, d_out,
+                                           nullptr);
+    k_pairs_sparse<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
+                                                g.ncount.p, d_out, nullptr);
+    S.kernel_launches += 16 + (end_bit + 7) / 8;
     TRACS_CK(cudaGetLastError());
-    return;
   }
-  // ---- components of the candidate graph ----------------------------------------------------------------------
-  DevBuf<uint32_t> parent(n), iota(n), size(n), ecnt(n), ntasks(n + 1), task_off(n + 1), dense_list(n), n_dense(1), sroot(n), members(n),
-      comp_start(n), rank(n);
-  DevBuf<uint64_t> msq(n + 1), sq_off(n + 1);
-  DevBuf<uint8_t> dense(n);
-  TRACS_CK(cudaMemsetAsync(size.p, 0, n * sizeof(uint32_t), st));
-  TRACS_CK(cudaMemsetAsync(ecnt.p, 0, n * sizeof(uint32_t), st));
-  TRACS_CK(cudaMemsetAsync(n_dense.p, 0, sizeof(uint32_t), st));
-  k_pp_init<<<grid1(n), 256, 0, st>>>(parent.p, iota.p, n);
-  k_pp_hook<<<grid1(E), 256, 0, st>>>(keys, E, parent.p);
-  k_pp_flatten<<<grid1(n), 256, 0, st>>>(parent.p, n, size.p);
-  k_pp_count<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, ecnt.p);
-  k_pp_decide<<<grid1((uint64_t)n + 1), 256, 0, st>>>(parent.p, size.p, ecnt.p, n, dense.p, ntasks.p, msq.p, dense_list.p, n_dense.p);
-  size_t tb1 = 0, tb2 = 0, tb3 = 0;
-  int end_bit = 1;
-  while ((1ull << end_bit) < n) end_bit++;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb1, ntasks.p, task_off.p, (int64_t)n + 1, st);
-  cub::DeviceScan::ExclusiveSum(nullptr, tb2, msq.p, sq_off.p, (int64_t)n + 1, st);
-  cub::DeviceRadixSort::SortPairs(nullptr, tb3, parent.p, sroot.p, iota.p, members.p, (int64_t)n, 0, end_bit, st);
-  DevBuf<uint8_t> tmp(std::max(tb1, std::max(tb2, tb3)));
-  cub::DeviceScan::ExclusiveSum(tmp.p, tb1, ntasks.p, task_off.p, (int64_t)n + 1, st);
-  cub::DeviceScan::ExclusiveSum(tmp.p, tb2, msq.p, sq_off.p, (int64_t)n + 1, st);
-  cub::DeviceRadixSort::SortPairs(tmp.p, tb3, parent.p, sroot.p, iota.p, members.p, (int64_t)n, 0, end_bit, st);  // stable: members stay in sample order
-  k_pp_heads<<<grid1(n), 256, 0, st>>>(sroot.p, n, comp_start.p);
-  k_pp_rank<<<grid1(n), 256, 0, st>>>(sroot.p, members.p, n, comp_start.p, rank.p);
-  // capacity bounds that need no round trip to the host: a dense component has m(m-1)/2 <= 4 x its candidates, so
-  // sum m^2 <= 8 E + n matrix entries, and (m/64 + 1)^2 block tasks
-  const uint64_t sq_cap = 8 * E + n + 16, task_cap = E / 256 + 2ull * n + 16;
-  DevBuf<uint2> tasks(task_cap);
-  DevBuf<uint32_t> scratch_d(sq_cap), scratch_i(u_out ? sq_cap : 1);
-  k_pp_tasks<<<grid1(n), 256, 0, st>>>(ntasks.p, task_off.p, size.p, n, tasks.p);
-  int dev = 0, n_sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned bgrid = (unsigned)std::min<uint64_t>(task_cap, (uint64_t)n_sm * 16);
-  k_block_d<0><<<bgrid, BD_THREADS, 0, st>>>(tasks.p, task_off.p, n, members.p, comp_start.p, size.p, sq_off.p, g.planesT.p, g.Wp, 1u, 1u,
-                                           scratch_d.p);
-  if (u_out) {
+
+  void unions(const Ingested &g, const uint64_t *keys, uint64_t E, uint32_t *u_out, cudaStream_t st) {
+    tracs_stats_t &S = g_stats;
+    if (E == 0 || !u_out) return;
+    if (!blocks) {
+      k_pairs_sparse<<<grid1(E), 256, 0, st>>>(keys, E, nullptr, nullptr, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
+                                                  g.ncount.p, nullptr, u_out);
+      S.kernel_launches++;
+      TRACS_CK(cudaGetLastError());
+      return;
+    }
     // N intersections: summary-guided (k_block_n) while most 128-site blocks are free of N; a dense AND + POPC
     // contraction over whole N-plane rows once they are not (estimated block occupancy 1 - (1 - p_N)^128 > 35 %)
     const char *nmode = getenv("TRACS_NBLOCKS");  // "dense" / "sparse": tests force both
@@ -470,6 +502,8 @@ static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint
     bool dense_n = 1.0 - pow(1.0 - std::min(1.0, p_n), 128.0) > 0.35;
     if (nmode && !strcmp(nmode, "dense")) dense_n = true;
     if (nmode && !strcmp(nmode, "sparse")) dense_n = false;
+    if (g.nplane_sparse) dense_n = false;  // only the 256-site groups that hold an N were stored: whole rows cannot be contracted
+    scratch_i.alloc(sq_cap);
     TRACS_CK(cudaMemsetAsync(scratch_i.p, 0, sq_cap * sizeof(uint32_t), st));
     if (dense_n) {
       const uint32_t ksplit = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, g.npitch / 4 / PP_KC / 64));  // >= 64 chunks per slice
@@ -480,13 +514,19 @@ static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint
       k_block_n<<<n_sm * 8, 256, 0, st>>>(dense_list.p, n_dense.p, members.p, comp_start.p, size.p, sq_off.p, g.nplane.p, g.npitch, g.nsum.p,
                                         g.spitch, scratch_i.p);
     }
+    k_pairs_gather<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, rank.p, size.p, sq_off.p, scratch_d.p, scratch_i.p, g.ncount.p, nullptr,
+                                           u_out);
+    k_pairs_sparse<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
+                                                g.ncount.p, nullptr, u_out);
+    S.kernel_launches += 4;
+    TRACS_CK(cudaGetLastError());
   }
-  k_pairs_gather<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, rank.p, size.p, sq_off.p, scratch_d.p, scratch_i.p, g.ncount.p, d_out,
-                                         u_out);
-  k_pairs_sparse<<<grid1(E), 256, 0, st>>>(keys, E, parent.p, dense.p, g.planesT.p, g.Wp, g.nplane.p, g.npitch, g.nsum.p, g.spitch,
-                                              g.ncount.p, d_out, u_out);
-  S.kernel_launches += 18 + (end_bit + 7) / 8;
-  TRACS_CK(cudaGetLastError());
+};
+
+static void eval_pairs(const Ingested &g, const uint64_t *keys, uint64_t E, uint32_t *d_out, uint32_t *u_out, cudaStream_t st) {
+  PairEval pe;
+  pe.distances(g, keys, E, d_out, st);
+  pe.unions(g, keys, E, u_out, st);
 }
 
 }  // namespace tracs

@@ -151,6 +151,107 @@ static void finish_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, c
   }
 }
 
+__global__ void k_finish_ncomp(const uint32_t *__restrict__ idx, const uint64_t *__restrict__ n_sel, const uint32_t *__restrict__ u,
+                               uint64_t L_total, uint64_t *__restrict__ ncomp) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < *n_sel) ncomp[e] = L_total - u[idx[e]];
+}
+
+// Single-GPU tail of a thresholded call: candidates (device, keys ascending) -> edge columns on the host, with the
+// copies of the finished columns UNDER the compared-sites kernels. The distances are complete after the first phase of
+// PairEval, so threshold, selection and the likelihood columns are enqueued right behind it, followed by the
+// compared-sites phase; while that runs (5 of the 7 ms of the refinement at C3), the host learns the edge count and
+// the auxiliary stream copies rows / cols / dist / likelihood columns (100 of the 140 MB). Only the compared-sites
+// column is copied after its kernel. No host synchronisation sits between two kernels of the main stream.
+static void eval_finish_overlapped(const Ingested &g, const uint64_t *keys, uint64_t n_keys, uint32_t *d, uint32_t *u, uint64_t n,
+                                   uint64_t L_total, const tracs_opts_t &o, TransLut *lut, HostEdges &out, cudaStream_t st) {
+  tracs_stats_t &S = g_stats;
+  if (n_keys == 0) return;
+  if (n_keys >= (1ull << 32)) throw std::runtime_error("too many candidates");
+  const bool want_n = u != nullptr, fuse = lut != nullptr;
+  cudaStream_t aux = aux_stream();
+  static thread_local cudaEvent_t ev_sel = nullptr, ev_aux = nullptr;
+  static thread_local uint64_t *h_E = nullptr;  // page-locked landing place of the edge count
+  if (!ev_sel) {
+    TRACS_CK(cudaEventCreateWithFlags(&ev_sel, cudaEventDisableTiming));
+    TRACS_CK(cudaEventCreateWithFlags(&ev_aux, cudaEventDisableTiming));
+    TRACS_CK(cudaHostAlloc((void **)&h_E, sizeof(uint64_t), cudaHostAllocDefault));
+  }
+  DeferredTimers DT(st);
+  PairEval pe;
+  DT.start(&S.ms_refine);
+  pe.distances(g, keys, n_keys, d, st);
+  DT.stop();
+  // ---- threshold + selection + likelihood columns, all sized by the candidate count (an upper bound) -------------
+  DT.start(&S.ms_sort);
+  DevBuf<uint8_t> flags(n_keys);
+  DevBuf<uint32_t> idx(n_keys), d_o(n_keys);
+  DevBuf<uint64_t> n_sel(1), keys_o(n_keys), rows(n_keys), cols(n_keys), dist(n_keys), nc(want_n ? n_keys : 1);
+  k_finish_flags<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(d, n_keys, o.dist, flags.p);
+  size_t tb = 0;
+  cub::CountingInputIterator<uint32_t> cnt_it(0);
+  cub::DeviceSelect::Flagged(nullptr, tb, cnt_it, flags.p, idx.p, n_sel.p, (int64_t)n_keys, st);
+  DevBuf<uint8_t> tmp(tb);
+  cub::DeviceSelect::Flagged(tmp.p, tb, cnt_it, flags.p, idx.p, n_sel.p, (int64_t)n_keys, st);
+  k_finish_gather<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(idx.p, n_sel.p, keys, d, nullptr, L_total, keys_o.p, d_o.p, rows.p, cols.p,
+                                                                   dist.p, nullptr);
+  S.kernel_launches += 4;
+  TRACS_CK(cudaGetLastError());
+  TRACS_CK(cudaMemcpyAsync(h_E, n_sel.p, 8, cudaMemcpyDeviceToHost, st));
+  DT.stop();
+  DevBuf<double> d_p0, d_eK, d_dt;
+  if (fuse) {
+    DT.start(&S.ms_trans);
+    d_p0.alloc(n_keys); d_eK.alloc(n_keys); d_dt.alloc(n_keys);
+    lut->apply(keys_o.p, d_o.p, n_keys, d_p0.p, d_eK.p, d_dt.p, st, n_sel.p);
+    DT.stop();
+  }
+  TRACS_CK(cudaEventRecord(ev_sel, st));
+  // ---- compared sites: enqueued before the host looks at the count ---------------------------------------------------
+  if (want_n) {
+    DT.start(&S.ms_refine);
+    pe.unions(g, keys, n_keys, u, st);
+    k_finish_ncomp<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(idx.p, n_sel.p, u, L_total, nc.p);
+    S.kernel_launches++;
+    TRACS_CK(cudaGetLastError());
+    DT.stop();
+  }
+  // ---- the finished columns leave while that runs ---------------------------------------------------------------------
+  TRACS_CK(cudaEventSynchronize(ev_sel));
+  const uint64_t E = *h_E;
+  S.n_edges += E;
+  if (E == 0) {
+    TRACS_CK(cudaStreamSynchronize(st));
+    return;
+  }
+  const size_t old = out.rows.size();
+  out.rows.resize(old + E); out.cols.resize(old + E); out.dist.resize(old + E);
+  if (want_n) out.ncomp.resize(old + E);
+  if (fuse) { out.p0_log.resize(old + E); out.eK.resize(old + E); out.datediff.resize(old + E); }
+  TRACS_CK(cudaStreamWaitEvent(aux, ev_sel, 0));
+  TRACS_CK(cudaMemcpyAsync(out.rows.data() + old, rows.p, E * 8, cudaMemcpyDeviceToHost, aux));
+  TRACS_CK(cudaMemcpyAsync(out.cols.data() + old, cols.p, E * 8, cudaMemcpyDeviceToHost, aux));
+  TRACS_CK(cudaMemcpyAsync(out.dist.data() + old, dist.p, E * 8, cudaMemcpyDeviceToHost, aux));
+  S.d2h_bytes += E * 24;
+  if (fuse) {
+    TRACS_CK(cudaMemcpyAsync(out.p0_log.data() + old, d_p0.p, E * 8, cudaMemcpyDeviceToHost, aux));
+    TRACS_CK(cudaMemcpyAsync(out.eK.data() + old, d_eK.p, E * 8, cudaMemcpyDeviceToHost, aux));
+    TRACS_CK(cudaMemcpyAsync(out.datediff.data() + old, d_dt.p, E * 8, cudaMemcpyDeviceToHost, aux));
+    S.d2h_bytes += E * 24;
+    out.has_trans = true;
+  }
+  TRACS_CK(cudaEventRecord(ev_aux, aux));
+  if (want_n) {
+    DT.start(&S.ms_d2h);
+    TRACS_CK(cudaMemcpyAsync(out.ncomp.data() + old, nc.p, E * 8, cudaMemcpyDeviceToHost, st));
+    S.d2h_bytes += E * 8;
+    DT.stop();
+  }
+  TRACS_CK(cudaStreamSynchronize(st));
+  TRACS_CK(cudaEventSynchronize(ev_aux));  // the device columns go back to the cache below
+  DT.resolve();
+}
+
 void site_shard_finish_device(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
                               uint64_t L_total, const tracs_opts_t &o, HostEdges &out, cudaStream_t st) {
   finish_candidates(dev_keys, dev_d, dev_union, n_keys, n, L_total, o, nullptr, out, st);

@@ -115,9 +115,13 @@ __device__ __forceinline__ uint32_t pack_nbit(uint32_t t) {
 
 // is-N word of one sample's 32 sites -> N-plane, per-sample N count (shared-memory counter) and block summary.
 // The summary byte is only computed and stored when the warp saw an N at all (the buffer is pre-zeroed).
+// SPARSE_N: the word is stored only when its 256-site group (8 lanes = one 32-byte sector of the row) holds an N. The
+// plane is only ever read where the block summaries say so (k_block_n, k_pairs_sparse, k_ncomp), so the rest of the
+// buffer may keep whatever it held: at p_N = 1e-3 three quarters of the plane's sectors are never written.
+template <bool SPARSE_N = false>
 __device__ __forceinline__ void pack_emit_n(uint32_t isn, uint32_t *np, uint8_t *sp, uint32_t *cnt, uint32_t lane) {
-  __stcs(np, isn);
   const uint32_t nz = __ballot_sync(0xFFFFFFFFu, isn != 0);
+  if (!SPARSE_N || ((nz >> (lane & 24u)) & 0xFFu)) __stcs(np, isn);
   if (nz) {
     const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, __popc(isn));
     if (lane == 0) {
@@ -133,6 +137,7 @@ __device__ __forceinline__ void pack_emit_n(uint32_t isn, uint32_t *np, uint8_t 
 
 // One sample's 32 sites: lookups, column AND, is-N word, N count and block summary. Lanes past the
 // end of the alignment carry 'N' bytes and validp == 0, so every lane of a warp runs the same code.
+template <bool SPARSE_N = false>
 __device__ __forceinline__ void pack_one_sample(const uint4 &a, const uint4 &b, uint32_t *np, uint8_t *sp, uint32_t *cnt,
                                                 const uint8_t *slut, uint32_t (&acc)[8], uint32_t validp, uint32_t lane) {
   uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
@@ -145,7 +150,7 @@ __device__ __forceinline__ void pack_one_sample(const uint4 &a, const uint4 &b, 
   // the four flag positions of a half are disjoint: OR them, then interleave the two halves
   const uint32_t f0 = m0 | m1 | m2 | m3, f1 = m4 | m5 | m6 | m7;
   const uint32_t isn = bsel(f1, f0 >> 4, 0xF0F0F0F0u) & validp;
-  pack_emit_n(isn, np, sp, cnt, lane);
+  pack_emit_n<SPARSE_N>(isn, np, sp, cnt, lane);
 }
 
 // `rows` consecutive samples of one 32-site word. Running pointers (no 64-bit index arithmetic per sample);
@@ -251,6 +256,7 @@ k_pack(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint6
 // (and for the first chunk).
 constexpr int PACKX_AHEAD = 1;  // batches between the L2 prefetch and the loads
 
+template <bool SPARSE_N>
 __global__ void __launch_bounds__(PACK_THREADS, 3)
 k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uint64_t L, uint64_t pitch, uint32_t *__restrict__ colmask,
          uint32_t *__restrict__ nplane, uint64_t npitch /*words*/, uint8_t *__restrict__ nsum, uint64_t spitch /*bytes*/,
@@ -344,7 +350,7 @@ k_pack_x(const uint8_t *__restrict__ seqs, uint64_t s_begin, uint64_t s_end, uin
           *reinterpret_cast<uint4 *>(mine + t * 1024 + 512) = vb[t];
         }
         if (FULL || (uint32_t)t < rows)
-          pack_one_sample(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, slut, acc, validp, lane);
+          pack_one_sample<SPARSE_N>(va[t], vb[t], np + (size_t)t * npitch, sp + (size_t)t * spitch, cnt + t, slut, acc, validp, lane);
       }
       if (nE) {  // warp-uniform
         __syncwarp();
@@ -1145,30 +1151,33 @@ k_ncomp(const uint64_t *__restrict__ keys, uint64_t E, const uint32_t *__restric
 // src/transcluster.hpp:245-274 is (d, |day_i - day_j|): a dense table indexed d * DD + dd.
 //   mark used keys -> compact -> one thread per used key runs the series -> per-edge gather
 // ------------------------------------------------------------------------------------------
+// (E_dev != nullptr: the edge count lives on the device, E is the launch's upper bound)
 __global__ void k_trans_mark(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ dvals, uint64_t E,
-                             const int32_t *__restrict__ days, uint32_t DD, uint8_t *__restrict__ used) {
+                             const uint64_t *__restrict__ E_dev, const int32_t *__restrict__ days, uint32_t DD,
+                             uint8_t *__restrict__ used) {
   const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  if (e >= (E_dev ? *E_dev : E)) return;
   const uint64_t k = keys[e];
   const int32_t dd = abs(days[k >> 32] - days[k & 0xFFFFFFFFull]);
   uint8_t *u = used + (uint64_t)dvals[e] * DD + (uint32_t)dd;
   if (!*u) *u = 1;  // millions of edges share a few thousand keys: read first, the stores all hit the same lines
 }
-__global__ void k_trans_table(const uint32_t *__restrict__ key_idx, const uint64_t *__restrict__ n_keys, uint32_t DD,
+// key_idx == nullptr: the whole table (n_all entries), else the *n_keys listed entries
+__global__ void k_trans_table(const uint32_t *__restrict__ key_idx, const uint64_t *__restrict__ n_keys, uint64_t n_all, uint32_t DD,
                               const double *__restrict__ lg, double lamb, double beta, double thr,
                               double *__restrict__ p0_lut, double *__restrict__ eK_lut) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= *n_keys) return;
-  const uint32_t id = key_idx[t];
+  if (t >= (key_idx ? *n_keys : n_all)) return;
+  const uint32_t id = key_idx ? key_idx[t] : (uint32_t)t;
   const double delta = ((double)(id % DD) * 86400.0) / 31556952.0;  // == |t_i - t_j| / SECONDS_IN_YEAR
   trans_eval((int64_t)(id / DD), delta, lg, lamb, beta, thr, &p0_lut[id], &eK_lut[id]);
 }
 __global__ void k_trans_gather(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ dvals, uint64_t E,
-                               const int32_t *__restrict__ days, uint32_t DD, const double *__restrict__ p0_lut,
-                               const double *__restrict__ eK_lut, double *__restrict__ p0, double *__restrict__ eK,
-                               double *__restrict__ dt) {
+                               const uint64_t *__restrict__ E_dev, const int32_t *__restrict__ days, uint32_t DD,
+                               const double *__restrict__ p0_lut, const double *__restrict__ eK_lut, double *__restrict__ p0,
+                               double *__restrict__ eK, double *__restrict__ dt) {
   const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  if (e >= (E_dev ? *E_dev : E)) return;
   const uint64_t k = keys[e];
   const int32_t dd = abs(days[k >> 32] - days[k & 0xFFFFFFFFull]);
   const uint64_t id = (uint64_t)dvals[e] * DD + (uint32_t)dd;
@@ -1262,6 +1271,9 @@ struct Ingested {
   bool partial_ambiguity = false;      // some variable site carries a 2- or 3-base IUPAC code
   uint64_t n_total = 0;                // N / gap / unknown sites over all samples (sum of ncount)
   bool has_n_var = true;               // some sample is N at some variable site (the tensor-core sweep needs its N plane)
+  // Sparse N (decided on the first chunk of the early-extraction ingest): only the 256-site groups of the N bit-plane
+  // that hold an N were stored; everything else in the buffer is undefined and never read (summary-guided consumers).
+  bool nplane_sparse = false;
 };
 
 __global__ void k_sum_u32(const uint32_t *__restrict__ v, uint64_t n, unsigned long long *out) {
@@ -1293,7 +1305,20 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
   DevBuf<uint32_t> colmask(std::max<uint64_t>(1, Lw * 4));
   DevBuf<uint32_t> &nplane = g.nplane, &ncount = g.ncount;
   DevBuf<uint8_t> &nsum = g.nsum;
-  // N-plane is always produced by the pack pass (same pass over the ASCII bytes)
+  // Early extraction (see k_pack_x): pack a first chunk of samples, list the sites that already vary, and let the
+  // pack of all other samples store those sites' masks on the way. TRACS_INGEST=split / =early overrides the rule.
+  const char *mode_env = getenv("TRACS_INGEST");
+  const uint64_t n_first = PACK_SCHUNK;
+  bool early = L >= (1u << 16) && n >= 4 * n_first && L < (1ull << 31);
+  if (mode_env && !strcmp(mode_env, "split")) early = false;
+  if (mode_env && !strcmp(mode_env, "early")) early = L > 0 && n > n_first && L < (1ull << 31);
+  // The N-plane comes out of the pack pass (same pass over the bytes). On the early-extraction path the first chunk's N
+  // counts tell whether N is sparse; if so, the main launch stores only the sectors that hold an N (pack_emit_n<true>).
+  // TRACS_NPLANE=always / sparse overrides the density rule; TRACS_NBLOCKS=dense (tests) wants whole rows.
+  const char *np_env = getenv("TRACS_NPLANE");
+  const char *nb_env = getenv("TRACS_NBLOCKS");
+  const bool sparse_candidate = early && !(np_env && !strcmp(np_env, "always")) && !(nb_env && !strcmp(nb_env, "dense"));
+  g.nplane_sparse = false;
   nplane.alloc(n * npitch);
   nsum.alloc(n * spitch);
   ncount.alloc(n);
@@ -1325,8 +1350,12 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
     if (sb <= sa) return;
     dim3 grid((unsigned)((npitch + PACK_THREADS - 1) / PACK_THREADS), (unsigned)((sb - sa + PACK_SCHUNK - 1) / PACK_SCHUNK));
     if (packed) {
-      if (VE) {
-        TRACS_CK(cudaFuncSetAttribute(k_pack4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+      if (VE && g.nplane_sparse) {
+        TRACS_CK(cudaFuncSetAttribute((k_pack4<true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+        k_pack4<true, true><<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch,
+                                                         ncount.p, elist, VE, X, XP);
+      } else if (VE) {
+        TRACS_CK(cudaFuncSetAttribute((k_pack4<true, false>), cudaFuncAttributePreferredSharedMemoryCarveout, 60));
         k_pack4<true><<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p,
                                                    elist, VE, X, XP);
       } else {
@@ -1334,22 +1363,20 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
                                                     nullptr, 0, nullptr, 0);
       }
     } else if (VE) {
-      TRACS_CK(cudaFuncSetAttribute(k_pack_x, cudaFuncAttributePreferredSharedMemoryCarveout, 60));  // 3 x 34 KB per SM (per device)
-      k_pack_x<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p, elist,
-                                            VE, X, XP);
+      TRACS_CK(cudaFuncSetAttribute(k_pack_x<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));  // 3 x 34 KB per SM (per device)
+      TRACS_CK(cudaFuncSetAttribute(k_pack_x<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+      if (g.nplane_sparse)
+        k_pack_x<true><<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p,
+                                                    elist, VE, X, XP);
+      else
+        k_pack_x<false><<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p,
+                                                     elist, VE, X, XP);
     } else {
       k_pack<<<grid, PACK_THREADS, 0, st>>>(dev_seqs, sa, sb, L, pitch, colmask.p, nplane.p, npitch, nsum.p, spitch, ncount.p);
     }
     S.kernel_launches++;
     TRACS_CK(cudaGetLastError());
   };
-  // Early extraction (see k_pack_x): pack a first chunk of samples, list the sites that already vary, and let the
-  // pack of all other samples store those sites' masks on the way. TRACS_INGEST=split / =early overrides the rule.
-  const char *mode_env = getenv("TRACS_INGEST");
-  const uint64_t n_first = PACK_SCHUNK;
-  bool early = L >= (1u << 16) && n >= 4 * n_first && L < (1ull << 31);
-  if (mode_env && !strcmp(mode_env, "split")) early = false;
-  if (mode_env && !strcmp(mode_env, "early")) early = L > 0 && n > n_first && L < (1ull << 31);
   DevBuf<uint32_t> elist;
   DevBuf<uint8_t> X;
   uint64_t VE = 0, XP = 0;
@@ -1362,6 +1389,9 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
     S.ms_pack_main += Tm.stop();
   } else {
     launch_pack(0, n_first, nullptr, 0, nullptr, 0);
+    std::vector<uint32_t> first_cnt(sparse_candidate ? n_first : 0);
+    if (sparse_candidate)  // lands with the synchronisation inside select_sites
+      TRACS_CK(cudaMemcpyAsync(first_cnt.data(), ncount.p, n_first * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     VE = select_sites(elist);
     if (VE > L / 16) VE = 0;  // very diverse alignment: the scattered pass reads dense lines anyway
     if (VE) {
@@ -1369,6 +1399,16 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
       X.alloc(n * XP);
     } else {
       early = false;
+    }
+    if (sparse_candidate && VE) {
+      // same rule as the choice between the summary-guided and the dense compared-sites kernels (pairs.inl): sparse
+      // while fewer than 35 % of the 128-site blocks hold an N
+      double tot = 0;
+      for (uint32_t c : first_cnt) tot += c;
+      const double p_n = tot / ((double)n_first * (double)L);
+      g.nplane_sparse = 1.0 - pow(1.0 - std::min(1.0, p_n), 128.0) <= 0.35;
+      if (np_env && !strcmp(np_env, "sparse")) g.nplane_sparse = true;
+      if (g.nplane_sparse) S.sparse_nplane = 1.0f;
     }
     Timer Tm(st);
     Tm.start();
@@ -1444,7 +1484,9 @@ static void ingest_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint6
 
 // Fused transmission likelihood (K3) for a sorted device edge list: dense table over (d, day difference).
 struct TransLut {
-  bool on = false;
+  static constexpr uint64_t EAGER_MAX = 16384;
+  bool on = false, eager = false;
+  cudaEvent_t ready = nullptr;
   uint32_t DD = 0;
   uint64_t lut_size = 0;
   double lamb = 0, beta = 0, thr = 0;
@@ -1475,22 +1517,50 @@ struct TransLut {
     const auto lg_keep = lgamma_table(nlg);
     d_lg.alloc(nlg);
     TRACS_CK(cudaMemcpyAsync(d_lg.p, lg_keep->data(), nlg * 8, cudaMemcpyHostToDevice, st));
-    p0_lut.alloc(lut_size); eK_lut.alloc(lut_size); used.alloc(lut_size); key_idx.alloc(lut_size); n_keys.alloc(1);
+    p0_lut.alloc(lut_size); eK_lut.alloc(lut_size);
+    if (lut_size <= EAGER_MAX) {
+      // small table (C2 / C3: 21 distances x 180 day differences): every entry is computed right away on the auxiliary
+      // stream, under the ingest, instead of mark -> compact -> table behind the last kernel of the call
+      eager = true;
+      cudaStream_t aux = aux_stream();
+      if (!ready) TRACS_CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+      TRACS_CK(cudaEventRecord(ready, st));  // the two uploads above
+      TRACS_CK(cudaStreamWaitEvent(aux, ready, 0));
+      k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, aux>>>(nullptr, nullptr, lut_size, DD, d_lg.p, lamb, beta, thr, p0_lut.p,
+                                                                   eK_lut.p);
+      g_stats.kernel_launches++;
+      TRACS_CK(cudaGetLastError());
+      TRACS_CK(cudaEventRecord(ready, aux));
+      return true;
+    }
+    used.alloc(lut_size); key_idx.alloc(lut_size); n_keys.alloc(1);
     cub::CountingInputIterator<uint32_t> cnt_it(0);
     cub::DeviceSelect::Flagged(nullptr, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
     sel_tmp.alloc(sel_tmp_bytes);
     return true;
   }
-  // keys (i << 32 | j) and distances of E edges -> log p0, E[K], date difference (years), all device arrays
-  void apply(const uint64_t *keys, const uint32_t *dvals, uint64_t E, double *p0, double *eK, double *dt, cudaStream_t st) {
-    TRACS_CK(cudaMemsetAsync(used.p, 0, lut_size, st));
-    k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys, dvals, E, d_days.p, DD, used.p);
-    cub::CountingInputIterator<uint32_t> cnt_it(0);
-    cub::DeviceSelect::Flagged(sel_tmp.p, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
-    k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, st>>>(key_idx.p, n_keys.p, DD, d_lg.p, lamb, beta, thr, p0_lut.p, eK_lut.p);
-    k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys, dvals, E, d_days.p, DD, p0_lut.p, eK_lut.p, p0, eK, dt);
-    g_stats.kernel_launches += 5;
+  // keys (i << 32 | j) and distances of E edges -> log p0, E[K], date difference (years), all device arrays.
+  // E_dev != nullptr: the count is read on the device and E is only an upper bound (no host round trip before this).
+  void apply(const uint64_t *keys, const uint32_t *dvals, uint64_t E, double *p0, double *eK, double *dt, cudaStream_t st,
+             const uint64_t *E_dev = nullptr) {
+    if (E == 0) return;
+    if (eager) {
+      TRACS_CK(cudaStreamWaitEvent(st, ready, 0));
+    } else {
+      TRACS_CK(cudaMemsetAsync(used.p, 0, lut_size, st));
+      k_trans_mark<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys, dvals, E, E_dev, d_days.p, DD, used.p);
+      cub::CountingInputIterator<uint32_t> cnt_it(0);
+      cub::DeviceSelect::Flagged(sel_tmp.p, sel_tmp_bytes, cnt_it, used.p, key_idx.p, n_keys.p, (int64_t)lut_size, st);
+      k_trans_table<<<(unsigned)((lut_size + 63) / 64), 64, 0, st>>>(key_idx.p, n_keys.p, 0, DD, d_lg.p, lamb, beta, thr, p0_lut.p, eK_lut.p);
+      g_stats.kernel_launches += 4;
+    }
+    k_trans_gather<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(keys, dvals, E, E_dev, d_days.p, DD, p0_lut.p, eK_lut.p, p0, eK, dt);
+    g_stats.kernel_launches += 1;
     TRACS_CK(cudaGetLastError());
+  }
+  ~TransLut() {
+    if (eager) cudaStreamSynchronize(aux_stream());  // the table kernel must not outlive the buffers it writes
+    if (ready) cudaEventDestroy(ready);
   }
 };
 
@@ -1525,8 +1595,8 @@ static TilePlan plan_tiles(uint64_t n, uint64_t i_end, uint64_t j_start, uint32_
 #include "pairs.inl"
 namespace tracs {
 
-static void finish_candidates(const uint64_t *dev_keys, const uint32_t *dev_d, const uint32_t *dev_union, uint64_t n_keys, uint64_t n,
-                              uint64_t L_total, const tracs_opts_t &o, TransLut *lut_in, HostEdges &out, cudaStream_t st);
+static void eval_finish_overlapped(const Ingested &g, const uint64_t *keys, uint64_t n_keys, uint32_t *d, uint32_t *u, uint64_t n,
+                                   uint64_t L_total, const tracs_opts_t &o, TransLut *lut, HostEdges &out, cudaStream_t st);
 
 // Sweeps the device-resident ASCII matrix and appends edges (sorted) to `out`.
 void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitch, const tracs_opts_t &o,
@@ -1697,9 +1767,8 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
             cub::DeviceRadixSort::SortKeys(sort_tmp.p, kb, keys.p, keys2.p, (int64_t)n_cand, 0, end_bit, st);
             S.kernel_launches += 2 + (end_bit + 7) / 8;
             DevBuf<uint32_t> u_full(want_n ? n_cand : 1);
-            eval_pairs(ing, keys2.p, n_cand, dv2.p, want_n ? u_full.p : nullptr, st);
             S.ms_refine += T.stop();
-            finish_candidates(keys2.p, dv2.p, want_n ? u_full.p : nullptr, n_cand, n, L, o, fuse_trans ? &lut : nullptr, out, st);
+            eval_finish_overlapped(ing, keys2.p, n_cand, dv2.p, want_n ? u_full.p : nullptr, n, L, o, fuse_trans ? &lut : nullptr, out, st);
             handled = true;
           } else if (n_cand) {
             T.start();
