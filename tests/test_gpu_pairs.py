@@ -108,7 +108,7 @@ def test_dense_and_sparse_N_intersections_agree(oracle_mod, monkeypatch, p_N):
 
 
 @pytest.mark.parametrize("n,L,p_var,p_N,dist,expect_refine", [(600, 150_001, 0.06, 0.002, 25, True), (1100, 140_000, 0.06, 0.01, 25, True),
-                                                              (400, 99_999, 0.10, 0.0, 20, True), (520, 66_030, 0.06, 0.002, 2000, False)])
+                                                              (400, 160_001, 0.06, 0.0, 20, True), (520, 66_030, 0.06, 0.002, 2000, False)])
 def test_sparse_nplane_stores_match_oracle(oracle_mod, monkeypatch, n, L, p_var, p_N, dist, expect_refine):
     """Sparse N on the early-extraction ingest: the main launch stores only the 256-site groups of the N bit-plane that hold
     an N (pack_emit_n<true>); the rest of the buffer is stale and must never be read. The buffer is first filled with
@@ -143,7 +143,7 @@ def test_sparse_nplane_stores_match_oracle(oracle_mod, monkeypatch, n, L, p_var,
 def test_dense_N_keeps_whole_rows(oracle_mod, monkeypatch):
     """N-rich packed input (BASELINE configs[3] shape): the first chunk shows dense N, every N-plane word is stored and the
     dense contraction (k_block_d<1>) runs."""
-    s = synth.generate(700, 80_000, p_var=0.08, n_clusters=30, mu=4, p_N=0.3, p_amb=0.02, seed=5, gaps=2)
+    s = synth.generate(700, 80_000, p_var=0.05, n_clusters=30, mu=4, p_N=0.3, p_amb=0.02, seed=5, gaps=2)
     orc = oracle_mod.pairsnp_ascii(s, dist=12, n_threads=8)
     monkeypatch.setenv("TRACS_INGEST", "early")
     res = tracs_b200.pairsnp_matrix(s, dist=12)

@@ -333,7 +333,7 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
           g_stats.kernel_launches++;
         }
         a.tile_table = d_table.p;
-        launch_tile_sweep(a, tc_ok && words > 16, st, g.has_n_var);
+        launch_tile_sweep(a, tc_ok && words >= tc_min_words(), st, g.has_n_var);
         TRACS_CK(cudaStreamSynchronize(st));  // rbs/prefix are reused by the next cut
         g_stats.n_tiles += tiles;
         k0 = k1;

@@ -672,17 +672,6 @@ __global__ void k_tile_table(const uint32_t *__restrict__ rb_list, const uint32_
   table[tile] = make_uint2(rb, max(rb, cb_min) + (tile - tile_prefix[lo]));
 }
 
-// acc[b >> 3][b & 7] of a register-resident 8 x 8 array (fully unrolled select: no local-memory spill)
-__device__ __forceinline__ uint32_t acc_at(const uint32_t (&acc)[8][8], int b) {
-  uint32_t v = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (b == i * 8 + j) v = acc[i][j];
-  return v;
-}
-
 constexpr int SWEEP_THREADS = 256;
 constexpr int STAGE_U4 = KC * TILE;  // uint4 per stage per side
 constexpr uint32_t PREFILTER_WORDS = 64;  // widest prefilter window: 2048 variable sites
@@ -699,6 +688,11 @@ static inline uint32_t first_window(int64_t dist) {
   if (dist < 43) return 8;
   return prefilter_words(dist);
 }
+// narrowest prefilter window that goes to the tensor-core kernel when the masks allow it (TRACS_TC_MIN_WORDS: experiments)
+static inline uint32_t tc_min_words() {
+  const char *e = getenv("TRACS_TC_MIN_WORDS");
+  return e ? (uint32_t)atoi(e) : 17u;
+}
 static inline uint32_t next_window(uint32_t pw) { return pw < 8 ? 8 : pw < 16 ? 16 : (pw < PREFILTER_WORDS ? PREFILTER_WORDS : 0); }
 constexpr size_t SWEEP_SMEM = (size_t)STAGES * 2 * STAGE_U4 * sizeof(uint4);
 
@@ -708,14 +702,38 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
   uint4 *scol = srow + (size_t)STAGES * STAGE_U4;          // [STAGES][KC][TILE]
   __shared__ __align__(8) uint64_t full[STAGES];
   __shared__ uint2 s_tile[4];  // coordinates of the tiles whose panels are in flight (written by the issuing thread)
+  // Hits of a thresholded sweep are parked here and leave in batches: a lane with a hit used to reserve its place in the
+  // global list with an atomic of its own, and its warp -- and through the chunk barrier the whole CTA -- sat out the
+  // round trip to L2 (about 1 000 clk, on nearly every tile of a prefilter launch: a third of the kernel's samples).
+  constexpr uint32_t HB_CAP = 1024, HB_FLUSH = 512, HB_LANE_MAX = 4;  // a tile parks at most 8 warps x 8 lanes x 4 entries
+  __shared__ uint64_t hb_key[HB_CAP];
+  __shared__ uint32_t hb_val[HB_CAP];
+  __shared__ uint32_t hb_count;
+  __shared__ unsigned long long hb_base;
 
   const uint32_t tid = threadIdx.x;
   const uint32_t tx = tid & 15, ty = tid >> 4;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    hb_count = 0;
   }
   __syncthreads();
+  // all threads, at a point where nobody appends (right after a chunk barrier / after the last tile)
+  auto flush_hits = [&]() {
+    const uint32_t cnt = hb_count;
+    if (tid == 0) hb_base = cnt ? atomicAdd(a.counter, (unsigned long long)cnt) : 0ull;
+    __syncthreads();
+    const unsigned long long base = hb_base;
+    for (uint32_t e = tid; e < cnt; e += SWEEP_THREADS)
+      if (base + e < a.cap) {
+        a.keys[base + e] = hb_key[e];
+        a.dvals[base + e] = hb_val[e];
+      }
+    __syncthreads();
+    if (tid == 0) hb_count = 0;
+    __syncthreads();
+  };
 
   // a window narrower than one stage (Wp = 4): one chunk per tile of which only the first Wp words are evaluated (the
   // copies still bring KC words; the planes always hold at least KC)
@@ -728,32 +746,38 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
   // chunks per tile and would otherwise expose the full load latency on every tile).
   const uint32_t my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const uint32_t total_chunks = my_tiles * nk;
-  auto issue = [&](uint32_t g) {
-    const uint32_t t_iter = g / nk, chunk = g - t_iter * nk, slot = g % STAGES;
-    // the first chunk of a tile fetches its coordinates and parks them for everybody (read after a later barrier:
-    // at most ceil(STAGES / nk) <= 3 tiles are in flight, the ring holds 4)
-    uint2 rc;
-    if (chunk == 0) {
-      rc = __ldg(a.tile_table + blockIdx.x + t_iter * gridDim.x);
-      s_tile[t_iter & 3] = rc;
-    } else {
-      rc = s_tile[t_iter & 3];
+  // Requests are made by the 32 lanes of warp 0 TOGETHER: lane 0 arms the barrier, lanes 0..15 each start one of the 16
+  // bulk copies of a chunk, the position in the stream advances by counters (no division), and the coordinates of the
+  // next tile are fetched one request ahead. (One thread doing all of this serially -- a table load, two integer
+  // divisions, 16 address computations and copies, ~250 dependent instructions -- held warp 0, and through the chunk
+  // barrier the whole CTA, for about 2 000 clk per chunk: a third of a 4-word prefilter tile, a fifth of an 8-word chunk.)
+  const uint32_t warp_id = tid >> 5, lane_id = tid & 31;
+  uint32_t iss_g = 0, iss_t = 0, iss_c = 0, iss_slot = 0;  // next chunk to request: stream index, tile iteration, chunk, stage
+  uint2 rc_next = my_tiles ? __ldg(a.tile_table + blockIdx.x) : make_uint2(0u, 0u);  // coordinates of tile iteration iss_t
+  auto issue = [&]() {
+    const uint2 rc = rc_next;
+    uint64_t *bar = &full[iss_slot];
+    if (lane_id == 0) {
+      if (iss_c == 0) s_tile[iss_t & 3] = rc;  // parked for everybody (read after a later barrier: at most 3 tiles in flight, 4 slots)
+      mbar_expect_tx(bar, 2u * STAGE_U4 * (uint32_t)sizeof(uint4));
     }
-    const uint4 *grow = a.planes + (size_t)rc.x * TILE;
-    const uint4 *gcol = a.planes + (size_t)rc.y * TILE;
-    uint64_t *bar = &full[slot];
-    mbar_expect_tx(bar, 2u * STAGE_U4 * (uint32_t)sizeof(uint4));
-    uint4 *dr = srow + (size_t)slot * STAGE_U4;
-    uint4 *dc = scol + (size_t)slot * STAGE_U4;
-#pragma unroll
-    for (int kk = 0; kk < KC; ++kk) {
-      const size_t goff = (size_t)(chunk * KC + kk) * a.Npad;
-      bulk_g2s(dr + kk * TILE, grow + goff, TILE * sizeof(uint4), bar);
-      bulk_g2s(dc + kk * TILE, gcol + goff, TILE * sizeof(uint4), bar);
+    __syncwarp();
+    if (lane_id < 2u * KC) {
+      const uint32_t kk = lane_id >> 1;
+      const bool is_col = (lane_id & 1u) != 0u;
+      const uint4 *src = a.planes + (size_t)(is_col ? rc.y : rc.x) * TILE + (size_t)(iss_c * KC + kk) * a.Npad;
+      uint4 *dst = (is_col ? scol : srow) + (size_t)iss_slot * STAGE_U4 + kk * TILE;
+      bulk_g2s(dst, src, TILE * sizeof(uint4), bar);
+    }
+    ++iss_g;
+    iss_slot = iss_slot + 1 == (uint32_t)STAGES ? 0u : iss_slot + 1;
+    if (++iss_c == nk) {
+      iss_c = 0;
+      if (++iss_t < my_tiles) rc_next = __ldg(a.tile_table + blockIdx.x + (size_t)iss_t * gridDim.x);
     }
   };
-  if (tid == 0)
-    for (uint32_t g = 0; g < (uint32_t)STAGES && g < total_chunks; ++g) issue(g);
+  if (warp_id == 0)
+    while (iss_g < (uint32_t)STAGES && iss_g < total_chunks) issue();
   __syncthreads();
   uint32_t it = 0;  // running chunk counter
   uint32_t t_iter = 0;
@@ -789,8 +813,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
           }
         }
       }
-      __syncthreads();
-      if (tid == 0 && it + STAGES < total_chunks) issue(it + STAGES);
+      // The chunk barrier doubles as the vote on flushing the parked hits. Threads look at the counter BEFORE the
+      // barrier, while slower warps may still be appending the previous tile's hits (at most 256), so they may see
+      // different values: the OR makes the decision uniform, and a count above HB_FLUSH at one barrier is seen by
+      // everybody at the next one at the latest: the buffer never holds more than HB_FLUSH + 2 x 256 = HB_CAP entries.
+      const int want_flush = c + 1 == nk && *(volatile uint32_t *)&hb_count > HB_FLUSH;
+      const int do_flush = __syncthreads_or(want_flush);
+      if (warp_id == 0 && iss_g < total_chunks) issue();  // chunk it + STAGES
+      if (do_flush) flush_hits();
     }
 
     // ---- epilogue: threshold + append -------------------------------------------------
@@ -817,33 +847,53 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
     if (!hits) continue;
     if (__popc(hits) <= 8) {
       if (hit) {
-        uint32_t found = 0;
-        uint64_t keep1 = 0;
+        // Each of the few lanes with a hit walks ITS qualifying rows (usually one): the row is selected out of the 64
+        // accumulators once (8 x 8 predicated moves), its eight pairs are tested, and a pair that passes is parked.
+        // Different lanes work on different rows in the same trip. (Testing all 64 pairs into a bit mask and fetching
+        // each hit with a 64-way select afterwards cost ~500 instructions per warp and tile; parking from inside fully
+        // unrolled 8 x 8 loops was worse still: the compiler predicates the whole body 64 times.)
+        uint32_t rowmask = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if ((int32_t)(total_bits - rmax[i]) <= a.dist) {
-            const uint32_t gi = rb * TILE + i * 16 + ty;
+        for (int i = 0; i < 8; ++i) rowmask |= ((int32_t)(total_bits - rmax[i]) <= a.dist ? 1u : 0u) << i;
+        uint32_t parked = 0;
+        while (rowmask) {
+          const int i = __ffs(rowmask) - 1;
+          rowmask &= rowmask - 1;
+          uint32_t rv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t gj = cb * TILE + j * 16 + tx;
-              const int32_t d = (int32_t)(total_bits - acc[i][j]);
-              if (gi < a.i_end && gj < a.n && gj > gi && gj >= a.j_start && d <= a.dist) {
-                keep1 |= 1ull << (i * 8 + j);
-                found++;
+          for (int j = 0; j < 8; ++j) {
+            uint32_t v = acc[0][j];
+#pragma unroll
+            for (int ii = 1; ii < 8; ++ii) v = i == ii ? acc[ii][j] : v;
+            rv[j] = v;
+          }
+          const uint32_t gi = rb * TILE + (uint32_t)i * 16 + ty;
+          uint32_t keepj = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t gj = cb * TILE + j * 16 + tx;
+            const bool ok = (int32_t)(total_bits - rv[j]) <= a.dist && gi < a.i_end && gj < a.n && gj > gi && gj >= a.j_start;
+            keepj |= (ok ? 1u : 0u) << j;
+          }
+          while (keepj) {
+            const int j = __ffs(keepj) - 1;
+            keepj &= keepj - 1;
+            uint32_t v = rv[0];
+#pragma unroll
+            for (int jj = 1; jj < 8; ++jj) v = j == jj ? rv[jj] : v;
+            const uint64_t key = ((uint64_t)gi << 32) | (cb * TILE + (uint32_t)j * 16 + tx);
+            if (parked < HB_LANE_MAX) {
+              const uint32_t pos = atomicAdd(&hb_count, 1u);  // shared memory; < HB_CAP by construction
+              hb_key[pos] = key;
+              hb_val[pos] = total_bits - v;
+              ++parked;
+            } else {  // a lane with many hits: straight to the list
+              const unsigned long long pos = atomicAdd(a.counter, 1ull);
+              if (pos < a.cap) {
+                a.keys[pos] = key;
+                a.dvals[pos] = total_bits - v;
               }
             }
-          }
-        }
-        if (found) {
-          unsigned long long pos = atomicAdd(a.counter, (unsigned long long)found);
-          while (keep1) {
-            const int b = __ffsll((long long)keep1) - 1;
-            keep1 &= keep1 - 1;
-            if (pos < a.cap) {
-              a.keys[pos] = ((uint64_t)(rb * TILE + (b >> 3) * 16 + ty) << 32) | (cb * TILE + (b & 7) * 16 + tx);
-              a.dvals[pos] = total_bits - acc_at(acc, b);
-            }
-            pos++;
           }
         }
       }
@@ -895,6 +945,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) k_sweep(const SweepArgs a) {
       }
     }
   }
+  __syncthreads();
+  flush_hits();
 }
 
 // expand sorted keys into the output columns
@@ -1726,7 +1778,7 @@ void sweep_device(const uint8_t *dev_seqs, uint64_t n, uint64_t L, uint64_t pitc
       for (uint32_t pw = first; pw && !refined; pw = next_window(pw)) {
         a.Wp = pw;
         T.start();
-        launch_tile_sweep(a, tc_ok && pw > 16, st, ing.has_n_var);
+        launch_tile_sweep(a, tc_ok && pw >= tc_min_words(), st, ing.has_n_var);
         S.ms_sweep += T.stop();
         S.n_tiles += n_tiles;
         S.swept_wordpairs += units[b].pairs * pw;
