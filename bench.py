@@ -280,6 +280,22 @@ def hbm_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on the CPUs next to that GPU (NVML's ideal affinity) BEFORE any page-locked host memory is
+    allocated, so that every rank's host slab and result columns live on its GPU's NUMA node and the N concurrent
+    host <-> device streams do not all cross the socket interconnect. Returns what was done (goes into the JSON line)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = len(os.sched_getaffinity(0))
+        return "nvml ideal cpu affinity (%d -> %d cpus)" % (before, after)
+    except Exception as ex:   # containers may forbid it: measured as is
+        return "unchanged (%s)" % type(ex).__name__
+
+
 def kernel_traffic(config=None):
     """DRAM bytes per launch from the committed ncu captures (profiles/kernel_traffic.json), keyed by the config whose
     launch was captured: a figure is only attached to a launch of the same shape."""
@@ -488,6 +504,7 @@ def main():
     torch.cuda.set_device(local)
     _lib.check(_lib.lib().tracs_set_device(local))
     device = torch.device("cuda", local)
+    cpu_affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     dist_mod = None
     if world > 1:
         # keep NCCL's own banner / debug lines off stdout: the contract is ONE JSON line there
@@ -674,6 +691,8 @@ def main():
         line["cpu_baseline"] = {"value": None, "note": "timed at N=1 only"}
 
     if rank == 0:
+        if cpu_affinity:
+            line["cpu_affinity"] = cpu_affinity
         _emit(saved_stdout, line)
     if world > 1:
         dist_mod.barrier()

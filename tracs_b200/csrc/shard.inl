@@ -18,7 +18,14 @@ struct SiteShard {
   Ingested ing;
   DevBuf<uint64_t> cand;   // candidate keys (i << 32 | j) found by this rank, sorted
   uint64_t n_cand = 0;
+  // likelihood table prepared at open() when the options already carry the sampling days: it is computed on the
+  // auxiliary stream under the ingest, and the emit step of the same sweep picks it up (same days / parameters)
+  std::unique_ptr<TransLut> lut;
+  std::vector<int32_t> lut_days;
+  double lut_lamb = 0, lut_beta = 0, lut_thr = 0;
+  int32_t lut_dist = -1;
 };
+static thread_local SiteShard *g_open_shard = nullptr;  // the handle between open() and close() on this thread
 
 // finish: candidates with summed d <= dist, in key order
 __global__ void k_finish_flags(const uint32_t *__restrict__ d, uint64_t n, int32_t dist, uint8_t *__restrict__ flags) {
@@ -112,6 +119,12 @@ static bool emit_selection(Selection &sel, const HostColumns &dst, TransLut *lut
   S.d2h_bytes += E * (sel.want_n ? 32 : 24);
   TransLut lut_own;
   bool fuse = lut_in != nullptr;
+  if (!fuse && g_open_shard && g_open_shard->lut && sel.o.want_trans && sel.o.days && g_open_shard->lut_dist == sel.o.dist &&
+      g_open_shard->lut_lamb == sel.o.lamb && g_open_shard->lut_beta == sel.o.beta && g_open_shard->lut_thr == sel.o.threshold_Ek &&
+      g_open_shard->lut_days.size() == sel.n && !memcmp(g_open_shard->lut_days.data(), sel.o.days, sel.n * sizeof(int32_t))) {
+    lut_in = g_open_shard->lut.get();  // prepared at open()
+    fuse = true;
+  }
   if (!fuse) fuse = lut_own.setup(sel.o, sel.n, (uint64_t)std::max<int64_t>(sel.o.dist, 0) + 1, st);
   TransLut &lut = lut_in ? *lut_in : lut_own;
   DevBuf<double> d_p0, d_eK, d_dt;
@@ -283,6 +296,15 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
     std::unique_ptr<SiteShard> sh(new SiteShard());
     g_stats.n_samples = n;
     g_stats.seq_length = L_slab;
+    if (o.want_trans && o.days) {  // optional: the table kernel then runs under the ingest
+      sh->lut.reset(new TransLut());
+      if (sh->lut->setup(o, n, (uint64_t)o.dist + 1, st)) {
+        sh->lut_days.assign(o.days, o.days + n);
+        sh->lut_lamb = o.lamb; sh->lut_beta = o.beta; sh->lut_thr = o.threshold_Ek; sh->lut_dist = o.dist;
+      } else {
+        sh->lut.reset();
+      }
+    }
     ingest_device(dev_slab, n, L_slab, pitch, o.packed_input != 0, false, sh->ing, st);
     const Ingested &g = sh->ing;
     const uint64_t i_end = (o.i_end == 0 || o.i_end > n) ? n : o.i_end;
@@ -386,6 +408,7 @@ int tracs_site_shard_open(const uint8_t *dev_slab, size_t n, size_t L_slab, size
     g_stats.ms_total = Ttot.stop();
     *dev_cand_keys = sh->cand.p;
     *n_cand = nc;
+    g_open_shard = sh.get();
     *handle = sh.release();
   });
 }
@@ -438,7 +461,10 @@ int tracs_site_shard_emit(void *selection, const tracs_edges_t *dst, size_t at, 
 }
 
 int tracs_site_shard_close(void *handle) {
-  return guarded([&] { delete (SiteShard *)handle; });
+  return guarded([&] {
+    if (g_open_shard == (SiteShard *)handle) g_open_shard = nullptr;
+    delete (SiteShard *)handle;
+  });
 }
 
 }  // extern "C"

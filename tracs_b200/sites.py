@@ -45,10 +45,16 @@ class LibBackend:
         self.torch, self.device = torch, device
         self.slab_ptr, self.n, self.L_slab, self.pitch, self.packed = slab_ptr, n, L_slab, pitch, packed
         self.h = None
+        self.trans = None
+
+    def prepare(self, days, lamb, beta, threshold_Ek):
+        """Optional, before open(): with the sampling days known up front the library computes the likelihood table on a
+        side stream while the slab is ingested (the emit step of the same sweep picks it up)."""
+        self.trans = dict(days=days, lamb=lamb, beta=beta, threshold_Ek=threshold_Ek) if days is not None else None
 
     def open(self, dist, rank, world):
         """-> (int64 device tensor of this rank's candidate keys, sorted; stats dict)"""
-        o, _ = api.make_opts(dist=dist, shard_rank=rank, shard_world=world, packed=self.packed)
+        o, _keep = api.make_opts(dist=dist, shard_rank=rank, shard_world=world, packed=self.packed, **(self.trans or {}))
         h, keys, cnt = C.c_void_p(), C.c_void_p(), C.c_size_t(0)
         _lib.check(_lib.lib().tracs_site_shard_open(C.c_void_p(self.slab_ptr), self.n, self.L_slab, self.pitch, C.byref(o), C.byref(h),
                                                     C.byref(keys), C.byref(cnt)))
@@ -195,6 +201,8 @@ def sweep(torch, dist_mod, device, rank, world, slab_ptr, n, L_slab, pitch, L_to
             marks.append((name, time.perf_counter()))
     try:
         mark("start")
+        if world > 1 and hasattr(be, "prepare"):
+            be.prepare(days, lamb, beta, threshold_Ek)
         mine, st_open = be.open(dist, rank, world)
         mark("open")
         keys = exchange_candidates(torch, dist_mod, device, world, mine)
