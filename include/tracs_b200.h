@@ -268,6 +268,9 @@ int tracs_int_peak(double out[8]);
  * out[0] = TOP/s with N = 128 (the shape k_sweep_tc issues), out[1] = TOP/s with N = 256,
  * out[2], out[3] = SM clock cycles per MMA for the two shapes. */
 int tracs_tc_peak(double out[4]);
+/* The same probe held for `seconds` (0.05 .. 10): out[0] = TOP/s over the second half of the run (what the pipe sustains under
+ * the board's power cap: the denominator for multi-second tensor-core kernels), out[1] = over the whole run. */
+int tracs_tc_peak_sustained(double seconds, double out[2]);
 
 #ifdef __cplusplus
 }

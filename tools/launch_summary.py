@@ -2,7 +2,7 @@
 """Per-step kernel shares from an ncu launch list (CSV with gpu__time_duration.sum, optionally dram__bytes_*).
 
 usage: tools/launch_summary.py launches.csv
-A step starts at the small first-chunk pack launch (tracs::k_pack for ASCII input, tracs::k_pack4<0> for packed
+A step starts at the small first-chunk pack launch (tracs::k_pack for ASCII input, tracs::k_pack4<0, ...> for packed
 input); the LAST complete step of the default (filter-and-refine) path is summarised -- bench.py also runs forced
 full-length sweeps for roofline_kernels, which are not part of the timed step."""
 import csv
@@ -27,7 +27,8 @@ def load(path):
 
 
 def is_step_start(name):
-    return name == "tracs::k_pack" or name.startswith("tracs::k_pack4<0>") or name.startswith("tracs::k_pack4<(bool)0>")
+    return (name == "tracs::k_pack" or name.startswith("tracs::k_pack4<0>") or name.startswith("tracs::k_pack4<0,")
+            or name.startswith("tracs::k_pack4<(bool)0"))
 
 
 def main():

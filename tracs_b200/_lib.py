@@ -53,7 +53,7 @@ SYMBOLS = ["tracs_pairsnp", "tracs_pairsnp_host", "tracs_pairsnp_device", "tracs
            "tracs_dev_free", "tracs_host_alloc_pinned", "tracs_host_free_pinned", "tracs_memcpy_d2h",
            "tracs_memcpy_h2d", "tracs_int_peak", "tracs_read_fasta", "tracs_free_fasta", "tracs_shard_rowblocks",
            "tracs_site_shard_open", "tracs_site_shard_partials", "tracs_site_shard_close", "tracs_connected_components",
-           "tracs_write_distance_csv", "tracs_float_repr", "tracs_pairsnp_packed", "tracs_encode_packed", "tracs_site_shard_finish", "tracs_tc_peak", "tracs_site_shard_select", "tracs_site_shard_emit",
+           "tracs_write_distance_csv", "tracs_float_repr", "tracs_pairsnp_packed", "tracs_encode_packed", "tracs_site_shard_finish", "tracs_tc_peak", "tracs_tc_peak_sustained", "tracs_site_shard_select", "tracs_site_shard_emit",
            "tracs_host_register", "tracs_host_unregister"]
 
 _lib = None
@@ -95,6 +95,7 @@ def lib():
         L.tracs_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.tracs_int_peak.argtypes = [C.c_void_p]
         L.tracs_tc_peak.argtypes = [C.c_void_p]
+        L.tracs_tc_peak_sustained.argtypes = [C.c_double, C.c_void_p]
         L.tracs_read_fasta.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                        C.POINTER(C.POINTER(C.c_char_p))]
         L.tracs_free_fasta.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_char_p), C.c_size_t]

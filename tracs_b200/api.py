@@ -227,5 +227,14 @@ def tc_peak():
             "source": "measured in this run (tracs_tc_peak: back-to-back tcgen05.mma kind::i8 M128 K32 on all SMs, N = 128 / 256, best shape)"}
 
 
+def tc_peak_sustained(seconds=2.0):
+    """The tensor-pipe probe held for `seconds`: TOP/s over the second half of the run (power-capped steady state)."""
+    out = np.zeros(2, np.float64)
+    _lib.check(_lib.lib().tracs_tc_peak_sustained(C.c_double(seconds), out.ctypes.data))
+    return {"tops": float(out[0]), "tops_whole_run": float(out[1]), "seconds": float(seconds),
+            "source": "measured in this run (tracs_tc_peak_sustained: back-to-back tcgen05.mma kind::i8 M128 N256 K32 on all SMs "
+                      "held for %.1f s, second half: the rate under the board's power cap)" % seconds}
+
+
 def last_stats():
     return _lib.last_stats()

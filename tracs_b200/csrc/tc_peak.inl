@@ -79,3 +79,40 @@ extern "C" int tracs_tc_peak(double out[4]) {
     run(256, out[1], out[3]);
   });
 }
+
+// The same probe held for `seconds` (back-to-back launches of the N = 256 shape): out[0] = TOP/s over the second half of
+// the run, out[1] = TOP/s over the whole run. A multi-second tensor-core kernel runs under the board's power cap
+// (sw_power_cap at ~1 kW on B200); the burst figure of tracs_tc_peak is not what the pipe can sustain then.
+extern "C" int tracs_tc_peak_sustained(double seconds, double out[2]) {
+  using namespace tracs;
+  return guarded([&] {
+    require_device();
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    DevBuf<long long> cyc(1);
+    const int reps = 100000;  // ~6.5 ms per launch
+    const size_t smem = (size_t)(128 + 256) * 32 + 1024;
+    const int launches = std::max(4, (int)(std::min(std::max(seconds, 0.05), 10.0) / 6.5e-3)) & ~1;
+    cudaEvent_t e0, e1, e2;
+    TRACS_CK(cudaEventCreate(&e0));
+    TRACS_CK(cudaEventCreate(&e1));
+    TRACS_CK(cudaEventCreate(&e2));
+    TRACS_CK(cudaEventRecord(e0, 0));
+    for (int i = 0; i < launches; ++i) {
+      if (i == launches / 2) TRACS_CK(cudaEventRecord(e1, 0));
+      k_tc_rate<256><<<n_sm, 128, smem>>>(reps, cyc.p);
+    }
+    TRACS_CK(cudaEventRecord(e2, 0));
+    TRACS_CK(cudaEventSynchronize(e2));
+    TRACS_CK(cudaGetLastError());
+    float ms_all = 0, ms_half = 0;
+    cudaEventElapsedTime(&ms_all, e0, e2);
+    cudaEventElapsedTime(&ms_half, e1, e2);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    const double ops = (double)n_sm * reps * 2.0 * 128.0 * 256.0 * 32.0;
+    out[0] = ops * (launches / 2) / ((double)ms_half * 1e-3) / 1e12;
+    out[1] = ops * launches / ((double)ms_all * 1e-3) / 1e12;
+  });
+}
+
