@@ -296,6 +296,35 @@ def bind_to_gpu_numa_node(index):
         return "unchanged (%s)" % type(ex).__name__
 
 
+def pinned_on_gpu_node(index, nbytes, _lib):
+    """A page-locked host buffer on the NUMA node the GPU hangs off (anonymous mmap + mbind + cudaHostRegister): with one
+    process per GPU streaming its slab, buffers that all sit on the node the container's CPUs belong to make half of the
+    GPUs read across the socket interconnect. Returns (uint8 numpy array or None, note)."""
+    import ctypes
+    import mmap
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None, "gpu numa node unknown"
+        m = mmap.mmap(-1, nbytes)
+        arr = np.frombuffer(m, dtype=np.uint8)
+        mask = (ctypes.c_ulong * 2)(0, 0)
+        mask[node // 64] = 1 << (node % 64)
+        libc = ctypes.CDLL(None, use_errno=True)
+        if libc.syscall(237, ctypes.c_void_p(arr.ctypes.data), ctypes.c_ulong(nbytes), 2, mask, ctypes.c_ulong(129), 0) != 0:  # SYS_mbind, MPOL_BIND
+            return None, "mbind to node %d refused (errno %d)" % (node, ctypes.get_errno())
+        _lib.check(_lib.lib().tracs_host_register(arr.ctypes.data, nbytes))
+        return arr, "mmap + mbind(node %d) + cudaHostRegister" % node
+    except Exception as ex:
+        return None, "unavailable (%s)" % type(ex).__name__
+
+
 def kernel_traffic(config=None):
     """DRAM bytes per launch from the committed ncu captures (profiles/kernel_traffic.json), keyed by the config whose
     launch was captured: a figure is only attached to a launch of the same shape."""
@@ -638,7 +667,12 @@ def main():
     if not args.no_e2e:
         e2e = {"value": None, "unit": "site-pairs/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}
         try:
-            host = torch.empty(inp.bytes, dtype=torch.uint8, pin_memory=True)
+            host_arr, host_note = pinned_on_gpu_node(local, inp.bytes, _lib) if world > 1 else (None, None)
+            if host_arr is not None:
+                host = torch.from_numpy(host_arr)
+            else:
+                host = torch.empty(inp.bytes, dtype=torch.uint8, pin_memory=True)
+            e2e["host_buffer"] = host_note or "cudaHostAlloc"
             host.copy_(inp.buf)
             torch.cuda.synchronize()
             hp = host.numpy()
@@ -665,6 +699,9 @@ def main():
                             "h2d_bytes_per_step": int(n * ((L + 1) // 2 if inp.packed else L)) if strong else int(n * width * replicas),
                             "d2h_bytes_per_step": int(st_e[-1].get("d2h_bytes", 0)), "host_memory": "pinned", "api": api,
                             "edges_equal_device_path": bool(all(np.array_equal(r2[k], res[k]) for k in ("rows", "cols", "dist", "ncomp")))})
+            if host_arr is not None:
+                torch.cuda.synchronize()
+                _lib.lib().tracs_host_unregister(host_arr.ctypes.data)
             del host
         except Exception as ex:  # report, never fake
             e2e["error"] = repr(ex)

@@ -234,16 +234,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_sweep_tc3(const SweepArgs a,
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           // d = W - matches = (3 W - T - 3 (cnt_i + cnt_j)) / 4 (exact)
           const int32_t cj_mine = NP == 4 ? 3 * (int32_t)__ldg(a.tc_ncnt + cb * TILE + c0 + lane) : 0;
-          {
-            // cheap rejection of the whole 32 x 32 chunk (nearly every chunk of a prefilter launch): d_j <= dist needs
-            // T_j + 3 cnt_j >= 3 W - 3 cnt_i - 4 dist - 3; bound the left side by max T + max 3 cnt
-            int32_t tmax = (int32_t)v[0];
-#pragma unroll
-            for (int j = 1; j < 32; j += 2) tmax = __vimax3_s32(tmax, (int32_t)v[j], (int32_t)v[j < 31 ? j + 1 : j]);
-            const int32_t cjmax = NP == 4 ? __reduce_max_sync(0xFFFFFFFFu, cj_mine) : 0;
-            const bool maybe = (long long)W3 - tmax - ci - cjmax <= 4ll * a.dist + 3;
-            if (!__any_sync(0xFFFFFFFFu, maybe)) continue;
-          }
           uint32_t keep = 0, cnt = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
