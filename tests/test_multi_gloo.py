@@ -130,18 +130,20 @@ def _sites_worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_site_sharded_exchange(oracle_mod):
-    """tracs_b200/sites.py at world_size 2 over gloo: slabs of one alignment, candidate all-gather, partial sums
-    all-reduced, finish on rank 0 -- equals the single-process oracle."""
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_rank_site_sharded_exchange(oracle_mod, world):
+    """tracs_b200/sites.py at world_size 2 and 3 over gloo: slabs of one alignment (uneven at 3), candidate all-gather,
+    partial sums summed over ranks, every rank finishes its slice of the candidates into the shared table (the last slice is
+    shorter at 3) -- equals the single-process oracle."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_sites_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 31500 + (os.getpid() * 7 + world) % 2000
+    procs = [ctx.Process(target=_sites_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=240) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in out), out
-    assert out[0][2] == out[1][2] > 0, out
+    assert len({c for _, _, c in out}) == 1 and out[0][2] > 0, out
