@@ -183,13 +183,18 @@ static void eval_finish_overlapped(const Ingested &g, const uint64_t *keys, uint
   if (n_keys >= (1ull << 32)) throw std::runtime_error("too many candidates");
   const bool want_n = u != nullptr, fuse = lut != nullptr;
   cudaStream_t aux = aux_stream();
-  static thread_local cudaEvent_t ev_sel = nullptr, ev_aux = nullptr;
+  // events belong to the device they were created on: one pair per device (a thread may drive several)
+  static thread_local cudaEvent_t ev_sel_dev[64] = {}, ev_aux_dev[64] = {};
   static thread_local uint64_t *h_E = nullptr;  // page-locked landing place of the edge count
-  if (!ev_sel) {
-    TRACS_CK(cudaEventCreateWithFlags(&ev_sel, cudaEventDisableTiming));
-    TRACS_CK(cudaEventCreateWithFlags(&ev_aux, cudaEventDisableTiming));
-    TRACS_CK(cudaHostAlloc((void **)&h_E, sizeof(uint64_t), cudaHostAllocDefault));
+  int cur_dev = 0;
+  TRACS_CK(cudaGetDevice(&cur_dev));
+  cur_dev &= 63;
+  if (!ev_sel_dev[cur_dev]) {
+    TRACS_CK(cudaEventCreateWithFlags(&ev_sel_dev[cur_dev], cudaEventDisableTiming));
+    TRACS_CK(cudaEventCreateWithFlags(&ev_aux_dev[cur_dev], cudaEventDisableTiming));
   }
+  if (!h_E) TRACS_CK(cudaHostAlloc((void **)&h_E, sizeof(uint64_t), cudaHostAllocPortable));
+  const cudaEvent_t ev_sel = ev_sel_dev[cur_dev], ev_aux = ev_aux_dev[cur_dev];
   DeferredTimers DT(st);
   PairEval pe;
   DT.start(&S.ms_refine);
