@@ -317,10 +317,12 @@ def pinned_on_gpu_node(index, nbytes, _lib):
         mask = (ctypes.c_ulong * 2)(0, 0)
         mask[node // 64] = 1 << (node % 64)
         libc = ctypes.CDLL(None, use_errno=True)
-        if libc.syscall(237, ctypes.c_void_p(arr.ctypes.data), ctypes.c_ulong(nbytes), 2, mask, ctypes.c_ulong(129), 0) != 0:  # SYS_mbind, MPOL_BIND
+        # SYS_mbind with MPOL_PREFERRED: pages come from the GPU's node while it has room and from elsewhere after that
+        # (MPOL_BIND would fail the allocation instead)
+        if libc.syscall(237, ctypes.c_void_p(arr.ctypes.data), ctypes.c_ulong(nbytes), 1, mask, ctypes.c_ulong(129), 0) != 0:
             return None, "mbind to node %d refused (errno %d)" % (node, ctypes.get_errno())
         _lib.check(_lib.lib().tracs_host_register(arr.ctypes.data, nbytes))
-        return arr, "mmap + mbind(node %d) + cudaHostRegister" % node
+        return arr, "mmap + mbind(preferred node %d) + cudaHostRegister" % node
     except Exception as ex:
         return None, "unavailable (%s)" % type(ex).__name__
 
