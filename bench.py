@@ -670,12 +670,23 @@ def main():
         e2e = {"value": None, "unit": "site-pairs/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}
         try:
             host_arr, host_note = pinned_on_gpu_node(local, inp.bytes, _lib) if world > 1 else (None, None)
+            host = None
             if host_arr is not None:
-                host = torch.from_numpy(host_arr)
-            else:
+                try:   # a first small round trip through the buffer; anything odd -> the plain page-locked allocation
+                    host = torch.from_numpy(host_arr)
+                    host[:4096].copy_(inp.buf.view(-1)[:4096])
+                    torch.cuda.synchronize()
+                except Exception as ex:
+                    host, host_note = None, "numa-placed buffer unusable (%s): cudaHostAlloc instead" % type(ex).__name__
+                    try:
+                        _lib.lib().tracs_host_unregister(host_arr.ctypes.data)
+                    except Exception:
+                        pass
+                    host_arr = None
+            if host is None:
                 host = torch.empty(inp.bytes, dtype=torch.uint8, pin_memory=True)
             e2e["host_buffer"] = host_note or "cudaHostAlloc"
-            host.copy_(inp.buf)
+            host.copy_(inp.buf.view(-1))
             torch.cuda.synchronize()
             hp = host.numpy()
             width = (inp.Ls + 1) // 2 if inp.packed else inp.Ls
@@ -702,8 +713,11 @@ def main():
                             "d2h_bytes_per_step": int(st_e[-1].get("d2h_bytes", 0)), "host_memory": "pinned", "api": api,
                             "edges_equal_device_path": bool(all(np.array_equal(r2[k], res[k]) for k in ("rows", "cols", "dist", "ncomp")))})
             if host_arr is not None:
-                torch.cuda.synchronize()
-                _lib.lib().tracs_host_unregister(host_arr.ctypes.data)
+                try:
+                    torch.cuda.synchronize()
+                    _lib.lib().tracs_host_unregister(host_arr.ctypes.data)
+                except Exception:
+                    pass
             del host
         except Exception as ex:  # report, never fake
             e2e["error"] = repr(ex)
